@@ -1,0 +1,290 @@
+"""Seeded synthetic model / input generator (SURVEY.md section 8d "Synthetic inputs").
+
+The reference ships no models and no test vectors, so every
+fixture is synthesised: an HTK-format tied-state triphone GMM acoustic model,
+an HMMList, a pronunciation dictionary, a forward 2-gram ARPA LM and HTK
+parameter files whose frames are sampled *from the model* along
+``<s> w .. </s>`` state paths (i.i.d. noise makes pass 1 fail).
+
+File formats follow the reference's readers:
+  hmmdefs   libsent/src/hmminfo/rdhmmdef_*.c          (HTK ASCII macros)
+  hmmlist   libsent/src/hmminfo/rdhmmlist.c:27-43     ("logical physical")
+  dict      libsent/src/voca/voca_load_htkdict.c:33-52
+  ARPA      libsent/src/ngram/ngram_read_arpa.c       (2-gram order = 1-gram listing order, :452-479)
+  features  libsent/src/anlz/rdparam.c:83-187         (big-endian HTK parameter file)
+
+This module only writes files / returns numpy arrays; it never calls the
+reference or the oracle.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import struct
+
+import numpy as np
+
+SIL = "sil"
+PARMKIND_MFCC_E_D_A = 6 | 0x40 | 0x100 | 0x200  # rdparam.c / htk_param.h
+PARMKIND_USER = 9
+
+
+@dataclasses.dataclass
+class SynthConfig:
+    name: str = "tiny"
+    seed: int = 1
+    n_phones: int = 8          # including sil (index 0)
+    n_states: int = 60         # tied-state pool size S
+    n_mix: int = 4             # M
+    dim: int = 39              # D
+    phys_per_phone: int = 6    # physical HMMs per centre phone
+    vocab: int = 50            # words excluding <s>, </s>
+    n_bigrams: int = 300
+    min_wlen: int = 2
+    max_wlen: int = 5
+    monophone: bool = False    # context-independent AM (config[0])
+    one_phone_words: int = 0   # number of 1-phone words (exercise AS_LRSET)
+
+    @staticmethod
+    def preset(name: str) -> "SynthConfig":
+        if name == "tiny":
+            return SynthConfig()
+        if name == "small":      # a few hundred words, used for CPU-side parity
+            return SynthConfig(name="small", seed=2, n_phones=12, n_states=240, n_mix=8,
+                               phys_per_phone=24, vocab=400, n_bigrams=4000,
+                               min_wlen=2, max_wlen=6, one_phone_words=3)
+        if name == "mono100":    # BASELINE config[0]: monophone 16-mix, 100 words
+            return SynthConfig(name="mono100", seed=3, n_phones=40, n_states=120, n_mix=16,
+                               phys_per_phone=1, vocab=100, n_bigrams=1500,
+                               min_wlen=2, max_wlen=6, monophone=True)
+        if name == "tri20k":     # BASELINE config[1]/[2]: 3k states x 16 mix, 20k words
+            return SynthConfig(name="tri20k", seed=4, n_phones=36, n_states=3000, n_mix=16,
+                               phys_per_phone=84, vocab=20000, n_bigrams=200000,
+                               min_wlen=3, max_wlen=8, one_phone_words=0)
+        raise KeyError(name)
+
+
+class SynthModel:
+    """Holds the generated AM/LM/dict as numpy arrays + writers for the HTK formats."""
+
+    def __init__(self, cfg: SynthConfig):
+        self.cfg = cfg
+        rng = np.random.default_rng(cfg.seed)
+        P, S, M, D = cfg.n_phones, cfg.n_states, cfg.n_mix, cfg.dim
+        self.phones = [SIL] + [f"p{i:02d}" for i in range(1, P)]
+        # ---- tied-state Gaussian pool (centre N(0,1) + N(0,0.5), var U(0.3,1.5), w Dirichlet(2))
+        centre = rng.normal(0.0, 1.0, size=(S, 1, D))
+        self.mean = (centre + rng.normal(0.0, 0.5, size=(S, M, D))).astype(np.float32)
+        self.var = rng.uniform(0.3, 1.5, size=(S, M, D)).astype(np.float32)
+        self.weight = rng.dirichlet(np.full(M, 2.0), size=S).astype(np.float32)
+        # ---- state pool partition by (centre phone, position)
+        part = [[[] for _ in range(3)] for _ in range(P)]
+        order = rng.permutation(S)
+        for i, s in enumerate(order):
+            part[(i // 3) % P][i % 3].append(int(s))
+        for c in range(P):
+            for k in range(3):
+                if not part[c][k]:
+                    part[c][k].append(int(order[(c * 3 + k) % S]))
+        # ---- physical models: (state triple, transition macro)
+        self.trans_names = ["T1", "T2", "T3"]
+        self.trans_self = [0.6, 0.5, 0.7]
+        K = cfg.phys_per_phone
+        self.phys = []           # list of (name, [s0,s1,s2], trans_idx)
+        self.phys_of = {}        # (c, h) -> phys index
+        for c in range(P):
+            for h in range(K):
+                st = [part[c][k][int(rng.integers(len(part[c][k])))] for k in range(3)]
+                self.phys_of[(c, h)] = len(self.phys)
+                self.phys.append((f"m{c:02d}_{h:03d}", st, int(rng.integers(3))))
+        self._ctx_hash = rng.integers(0, 1 << 30, size=(P, P))
+        # ---- vocabulary
+        V = cfg.vocab
+        self.words = []          # (name, [phone idx...])
+        seen = set()
+        n1 = cfg.one_phone_words
+        while len(self.words) < V:
+            if n1 > 0:
+                L = 1
+            else:
+                L = int(rng.integers(cfg.min_wlen, cfg.max_wlen + 1))
+            pr = tuple(int(x) for x in rng.integers(1, P, size=L))
+            if pr in seen:
+                continue
+            seen.add(pr)
+            if L == 1:
+                n1 -= 1
+            self.words.append((f"w{len(self.words):05d}", list(pr)))
+        # ---- LM: Zipf unigrams, random bigrams
+        rank = rng.permutation(V) + 1
+        p = 1.0 / rank.astype(np.float64)
+        p = 0.9 * p / p.sum()
+        self.lm_vocab = ["<unk>", "<s>", "</s>"] + [w for w, _ in self.words]
+        uni = np.concatenate([[1e-4, 0.01, 0.09], p])
+        self.uni_logp = np.log10(uni).astype(np.float32)
+        self.uni_bow = (-rng.uniform(0.05, 1.0, size=len(uni))).astype(np.float32)
+        nv = len(self.lm_vocab)
+        pairs = set()
+        nb = min(cfg.n_bigrams, (nv - 2) * (nv - 2) // 2)
+        while len(pairs) < nb:
+            k = nb - len(pairs)
+            w1 = rng.integers(1, nv, size=k * 2)
+            # Zipf-biased successor choice so that frequent words get bigrams
+            w2 = np.minimum(nv - 1, 2 + (rng.pareto(1.2, size=k * 2) * 20).astype(np.int64) % (nv - 2))
+            for a, b in zip(w1, w2):
+                if a == 2 or b == 1 or a == 0 or b == 0:   # no "</s> x", no "x <s>", no <unk>
+                    continue
+                pairs.add((int(a), int(b)))
+                if len(pairs) >= nb:
+                    break
+        self.bigrams = sorted(pairs)     # listing order == index order
+        self.bi_logp = (-rng.uniform(0.3, 4.0, size=len(self.bigrams))).astype(np.float32)
+        self.rng_state = rng
+
+    # ------------------------------------------------------------------ AM helpers
+    def triphone_phys(self, l: int, c: int, r: int) -> int:
+        if self.cfg.monophone:
+            return self.phys_of[(c, 0)]
+        h = int(self._ctx_hash[l, r]) % self.cfg.phys_per_phone
+        return self.phys_of[(c, h)]
+
+    def logical_name(self, l: int, c: int, r: int) -> str:
+        return f"{self.phones[l]}-{self.phones[c]}+{self.phones[r]}"
+
+    # ------------------------------------------------------------------ writers
+    def write_hmmdefs(self, path: str) -> None:
+        cfg = self.cfg
+        D, M = cfg.dim, cfg.n_mix
+        ln2pi = np.log(2.0 * np.pi)
+        with open(path, "w") as f:
+            f.write(f"~o\n<STREAMINFO> 1 {D}\n<VECSIZE> {D}<NULLD><MFCC_E_D_A><DIAGC>\n")
+            for name, a_self in zip(self.trans_names, self.trans_self):
+                a = np.zeros((5, 5))
+                a[0, 1] = 1.0
+                for i in (1, 2, 3):
+                    a[i, i] = a_self
+                    a[i, i + 1] = 1.0 - a_self
+                f.write(f'~t "{name}"\n<TRANSP> 5\n')
+                for row in a:
+                    f.write(" " + " ".join(f"{x:.6e}" for x in row) + "\n")
+            for s in range(cfg.n_states):
+                f.write(f'~s "st{s}"\n<NUMMIXES> {M}\n')
+                for m in range(M):
+                    f.write(f"<MIXTURE> {m + 1} {self.weight[s, m]:.8e}\n")
+                    f.write(f"<MEAN> {D}\n " + " ".join(f"{x:.8e}" for x in self.mean[s, m]) + "\n")
+                    f.write(f"<VARIANCE> {D}\n " + " ".join(f"{x:.8e}" for x in self.var[s, m]) + "\n")
+                    g = D * ln2pi + float(np.sum(np.log(self.var[s, m].astype(np.float64))))
+                    f.write(f"<GCONST> {g:.8e}\n")
+            for name, st, ti in self.phys:
+                f.write(f'~h "{name}"\n<BEGINHMM>\n<NUMSTATES> 5\n')
+                for k in range(3):
+                    f.write(f'<STATE> {k + 2}\n~s "st{st[k]}"\n')
+                f.write(f'~t "{self.trans_names[ti]}"\n<ENDHMM>\n')
+
+    def write_hmmlist(self, path: str) -> None:
+        P = self.cfg.n_phones
+        with open(path, "w") as f:
+            if self.cfg.monophone:
+                for c in range(P):
+                    f.write(f"{self.phones[c]} {self.phys[self.phys_of[(c, 0)]][0]}\n")
+                return
+            for l in range(P):
+                for c in range(P):
+                    for r in range(P):
+                        f.write(f"{self.logical_name(l, c, r)} {self.phys[self.triphone_phys(l, c, r)][0]}\n")
+
+    def write_dict(self, path: str) -> None:
+        with open(path, "w") as f:
+            f.write(f"<s> [] {SIL}\n</s> [] {SIL}\n")
+            for w, pr in self.words:
+                f.write(f"{w} [{w}] " + " ".join(self.phones[p] for p in pr) + "\n")
+
+    def write_arpa(self, path: str) -> None:
+        with open(path, "w") as f:
+            f.write("\n\\data\\\n")
+            f.write(f"ngram 1={len(self.lm_vocab)}\nngram 2={len(self.bigrams)}\n\n\\1-grams:\n")
+            for i, w in enumerate(self.lm_vocab):
+                f.write(f"{self.uni_logp[i]:.6f} {w} {self.uni_bow[i]:.6f}\n")
+            f.write("\n\\2-grams:\n")
+            for (a, b), lp in zip(self.bigrams, self.bi_logp):
+                f.write(f"{lp:.6f} {self.lm_vocab[a]} {self.lm_vocab[b]}\n")
+            f.write("\n\\end\\\n")
+
+    def write_all(self, outdir: str) -> dict:
+        os.makedirs(outdir, exist_ok=True)
+        paths = {k: os.path.join(outdir, k) for k in ("hmmdefs", "hmmlist", "dict", "lm.arpa")}
+        self.write_hmmdefs(paths["hmmdefs"])
+        self.write_hmmlist(paths["hmmlist"])
+        self.write_dict(paths["dict"])
+        self.write_arpa(paths["lm.arpa"])
+        return paths
+
+    # ------------------------------------------------------------------ features
+    def sample_utterance(self, rng: np.random.Generator, n_frames: int, noise: float = 1.0):
+        """Sample ~n_frames feature frames along a random ``<s> w.. </s>`` path.
+
+        Returns (feats [T, D] float32, word index list).  T is exactly n_frames:
+        words are appended until the budget is reached and the tail is padded
+        with trailing silence so every utterance ends inside ``</s>``.
+        """
+        cfg = self.cfg
+        states = []
+        words = []
+        avg = 3 * 2.5
+        budget = n_frames - int(6 * avg)
+
+        def add_phone(l, c, r):
+            ph = self.phys[self.triphone_phys(l, c, r)]
+            a_self = self.trans_self[ph[2]]
+            for s in ph[1]:
+                d = int(rng.geometric(1.0 - a_self))
+                states.extend([s] * d)
+
+        # <s>
+        seq = [[0]]
+        while True:
+            wi = int(rng.integers(len(self.words)))
+            seq.append(self.words[wi][1])
+            words.append(wi)
+            if sum(len(x) for x in seq) * avg >= budget:
+                break
+        seq.append([0])
+        flat = [p for w in seq for p in w]
+        for i, c in enumerate(flat):
+            l = flat[i - 1] if i > 0 else 0
+            r = flat[i + 1] if i + 1 < len(flat) else 0
+            add_phone(l, c, r)
+        sil_states = self.phys[self.triphone_phys(flat[-2] if len(flat) > 1 else 0, 0, 0)][1]
+        if len(states) > n_frames:
+            # cut inside the path but keep a silence tail of ~15 frames
+            tail = [sil_states[0]] * 5 + [sil_states[1]] * 5 + [sil_states[2]] * 5
+            states = states[: n_frames - len(tail)] + tail
+        while len(states) < n_frames:
+            states.append(sil_states[2])
+        st = np.asarray(states[:n_frames], dtype=np.int64)
+        comp = np.array([rng.choice(cfg.n_mix, p=self.weight[s].astype(np.float64) / float(self.weight[s].astype(np.float64).sum())) for s in st])
+        mu = self.mean[st, comp]
+        sd = np.sqrt(self.var[st, comp])
+        x = mu + noise * sd * rng.standard_normal(mu.shape).astype(np.float32)
+        return x.astype(np.float32), words
+
+    def sample_noise(self, rng: np.random.Generator, n_frames: int):
+        return rng.normal(0.0, 1.2, size=(n_frames, self.cfg.dim)).astype(np.float32)
+
+
+def write_htk_param(path: str, feats: np.ndarray, parmkind: int = PARMKIND_MFCC_E_D_A,
+                    samp_period: int = 100000) -> None:
+    """Big-endian HTK parameter file (libsent/src/anlz/rdparam.c:83-187)."""
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    T, D = feats.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack(">IIHh", T, samp_period, D * 4, parmkind))
+        f.write(feats.astype(">f4").tobytes())
+
+
+def read_htk_param(path: str):
+    with open(path, "rb") as f:
+        T, period, size, kind = struct.unpack(">IIHh", f.read(12))
+        D = size // 4
+        data = np.frombuffer(f.read(T * D * 4), dtype=">f4").astype(np.float32).reshape(T, D)
+    return data, kind
