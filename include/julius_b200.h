@@ -1,0 +1,135 @@
+/* julius_b200.h -- C-ABI of libjb200.so: B200-native acoustic scoring + pass-1 beam for Julius.
+ *
+ * Plain C: pointers, sizes, opaque handles.  No torch / CUDA types.  Every
+ * entry point names the reference interface it stands in for (file:line in
+ * julius-speech/julius 4.6); INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative error code; the message
+ *     is available from jb200_last_error() (thread-local).
+ *   - "host" variants take ordinary host pointers and include the H2D/D2H copies;
+ *     "device" variants take device pointers on the handle's device and enqueue
+ *     on the given CUDA stream (a cudaStream_t passed as void*; NULL = the
+ *     handle's own stream).
+ *   - scores are log10 likelihoods, exactly the values the reference keeps in
+ *     HMMWork.outprob_cache[t][state-id] (libsent/include/sent/hmm_calc.h:115).
+ *   - there is NO CPU fallback: creating a handle without a usable sm_100 GPU fails.
+ */
+#ifndef JULIUS_B200_H
+#define JULIUS_B200_H
+
+#include <stdint.h>
+#include "jb200_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB200_OK              0
+#define JB200_ERR_ARG        -1
+#define JB200_ERR_CUDA       -2
+#define JB200_ERR_NODEVICE   -3
+#define JB200_ERR_UNSUPPORTED -4
+#define JB200_ERR_CAPACITY   -5
+
+/* arithmetic mode of the GMM scorer */
+#define JB200_GMM_EXACT 0   /* reference's fp32 statement order + addlog table: bit-identical scores */
+#define JB200_GMM_FAST  1   /* FMA + exact log-sum-exp: <=1e-4 relative (BASELINE.json tolerance)  */
+
+int jb200_version(void);
+const char *jb200_last_error(void);
+int jb200_device_count(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+int64_t jb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * GMM state scorer.   Stands in for, per frame and for ALL states at once,
+ *   outprob_state()  libsent/src/phmm/outprob.c:183-249   (batch_computation branch :230-240)
+ *   calc_mix()       libsent/src/phmm/calc_mix.c:40-81
+ *   gprune_none/safe/beam/heu (compute_gaussset)  libsent/src/phmm/gprune_*.c
+ *   addlog_array()   libsent/src/phmm/addlog.c:102-123
+ *   outprob_cd()     libsent/src/phmm/outprob.c:286-400   (pseudo-phone sets)
+ * ---------------------------------------------------------------------------------- */
+typedef struct jb200_gmm jb200_gmm;
+
+int jb200_gmm_create(const jb200_gmm_desc *desc, int device, int mode, jb200_gmm **out);
+void jb200_gmm_destroy(jb200_gmm *h);
+/* row stride (floats) of the score matrix: n_states + n_cdsets rounded up to 4 */
+int jb200_gmm_score_stride(const jb200_gmm *h);
+int jb200_gmm_n_states(const jb200_gmm *h);
+int jb200_gmm_n_cdsets(const jb200_gmm *h);
+
+/* feats [T][dim] (host) -> scores [T][n_states] (host), log10. */
+int jb200_gmm_score_host(jb200_gmm *h, const float *feats, int T, float *scores);
+/* feats [T][dim] (host) -> full rows [T][stride] (host): states then cd-set scores */
+int jb200_gmm_score_rows_host(jb200_gmm *h, const float *feats, int T, float *rows);
+/* device: d_feats [T][dim] -> d_rows [T][stride]; state columns and cd-set columns are both filled */
+int jb200_gmm_score_device(jb200_gmm *h, const float *d_feats, int T, float *d_rows, void *stream);
+/* device: fill only the cd-set columns of rows whose state columns are already present */
+int jb200_gmm_cdsets_device(jb200_gmm *h, float *d_rows, int T, void *stream);
+/* per-Gaussian ln scores of ONE frame, without mixture weights (the calcmix hook's
+ * contract, plugin/calcmix.c:226-323): feat [dim] (host) -> gauss [n_gauss] (host) */
+int jb200_gmm_gauss_host(jb200_gmm *h, const float *feat, float *gauss);
+
+/* ------------------------------------------------------------------------------------
+ * Pass-1 decoder (lexicon-tree token passing).  Stands in for
+ *   get_back_trellis_init/_proceed/_end, finalize_1st_pass   libjulius/src/beam.c:1825,2663,3052,3133
+ *   outprob_style()                                         libjulius/src/outprob_style.c:354-494
+ *   max_successor_prob(_iw)()                               libjulius/src/factoring_sub.c:942-1143
+ *   bt_store/bt_relocate_rw/bt_sort_rw                      libjulius/src/backtrellis.c:190-267,438-478
+ * run for a whole BATCH of utterances, one thread-block per utterance, all frames
+ * inside one persistent kernel.
+ * ---------------------------------------------------------------------------------- */
+typedef struct jb200_decoder jb200_decoder;
+
+/* one word-trellis atom (libjulius/include/julius/trellis.h:28-45) */
+typedef struct {
+  int32_t wid;
+  int32_t begintime;
+  int32_t endtime;
+  float backscore;
+  float lscore;
+  int32_t last;        /* index of last_tre within the same utterance's atom list, -1 = sentence start */
+} jb200_atom;
+
+typedef struct {
+  int32_t status;      /* 0 = success, -1 = search failed (J_RESULT_STATUS_FAIL) */
+  int32_t n_frames;
+  int32_t n_atoms;
+  int32_t n_words;     /* pass-1 best sequence length */
+  float score;         /* pass1_score */
+  int64_t atom_offset; /* first atom of this utterance in the batch atom array */
+  int32_t word_offset; /* first word in the batch word array */
+  int32_t overflow;    /* non-zero if a device-side capacity was exceeded (result invalid) */
+} jb200_utt_result;
+
+/* am: GMM scorer (owns device + cd-set layout).  max_utts / max_frames size the work areas. */
+int jb200_decoder_create(const jb200_tree_desc *tree, jb200_gmm *am, int max_utts, int max_frames,
+                         jb200_decoder **out);
+void jb200_decoder_destroy(jb200_decoder *d);
+
+/* End-to-end: host feature vectors -> GPU scoring -> GPU beam -> host results.
+ *   feats       [sum T_u][dim]   concatenated utterances (host)
+ *   frame_off   [n_utts+1]       utterance boundaries in frames
+ * Results stay owned by the decoder until the next call; read them with jb200_decoder_results(). */
+int jb200_decode_batch_host(jb200_decoder *d, const float *feats, const int32_t *frame_off, int n_utts);
+/* Same, but the state-score matrix is given ([sum T_u][n_states], host, log10): used to
+ * check the beam in isolation on the reference's own score matrix. */
+int jb200_decode_batch_scores_host(jb200_decoder *d, const float *scores, const int32_t *frame_off, int n_utts);
+/* Device-resident input (bench "value"): d_feats on the decoder's device. */
+int jb200_decode_batch_device(jb200_decoder *d, const float *d_feats, const int32_t *frame_off, int n_utts);
+/* copy results of the last batch device->host (called implicitly by the *_host variants) */
+int jb200_decoder_fetch(jb200_decoder *d);
+int jb200_decoder_results(jb200_decoder *d, const jb200_utt_result **utts, const jb200_atom **atoms,
+                          const int32_t **words);
+/* timing of the last batch in milliseconds (CUDA events on the decoder's stream):
+ * [0]=H2D, [1]=acoustic scoring, [2]=beam, [3]=D2H */
+int jb200_decoder_last_timing(jb200_decoder *d, float ms[4]);
+/* per-frame token counts of utterance u of the last batch (debug / roofline accounting):
+ * counts [T][2] = (tokens created, survivors) */
+int jb200_decoder_frame_counts(jb200_decoder *d, int u, int32_t *counts, int max_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JULIUS_B200_H */

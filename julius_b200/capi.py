@@ -1,0 +1,206 @@
+"""ctypes binding of libjb200.so (include/julius_b200.h) -- the product's host-side mirror.
+
+Fails loudly when the CUDA library is missing or no B200 is visible: there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import desc as D
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libjb200.so")
+
+GMM_EXACT, GMM_FAST = 0, 1
+
+ATOM_DT = np.dtype([("wid", "<i4"), ("begin", "<i4"), ("end", "<i4"),
+                    ("backscore", "<f4"), ("lscore", "<f4"), ("last", "<i4")])
+UTT_DT = np.dtype([("status", "<i4"), ("n_frames", "<i4"), ("n_atoms", "<i4"), ("n_words", "<i4"),
+                   ("score", "<f4"), ("_pad", "<i4"), ("atom_offset", "<i8"), ("word_offset", "<i4"), ("overflow", "<i4")])
+
+_lib = None
+
+
+class Jb200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise Jb200Error(f"{LIBPATH} is missing: run `python -m julius_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(LIBPATH)
+        L.jb200_last_error.restype = C.c_char_p
+        L.jb200_launch_count.restype = C.c_int64
+        vp = C.c_void_p
+        L.jb200_gmm_create.argtypes = [C.POINTER(D.GmmDesc), C.c_int, C.c_int, C.POINTER(vp)]
+        L.jb200_gmm_destroy.argtypes = [vp]
+        for f in ("jb200_gmm_score_stride", "jb200_gmm_n_states", "jb200_gmm_n_cdsets"):
+            getattr(L, f).argtypes = [vp]
+        L.jb200_gmm_score_host.argtypes = [vp, D.F, C.c_int, D.F]
+        L.jb200_gmm_score_rows_host.argtypes = [vp, D.F, C.c_int, D.F]
+        L.jb200_gmm_score_device.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.jb200_gmm_cdsets_device.argtypes = [vp, vp, C.c_int, vp]
+        L.jb200_gmm_gauss_host.argtypes = [vp, D.F, D.F]
+        if hasattr(L, "jb200_decoder_create"):
+            L.jb200_decoder_create.argtypes = [C.POINTER(D.TreeDesc), vp, C.c_int, C.c_int, C.POINTER(vp)]
+            L.jb200_decoder_destroy.argtypes = [vp]
+            L.jb200_decode_batch_host.argtypes = [vp, D.F, D.I, C.c_int]
+            L.jb200_decode_batch_scores_host.argtypes = [vp, D.F, D.I, C.c_int]
+            L.jb200_decode_batch_device.argtypes = [vp, vp, D.I, C.c_int]
+            L.jb200_decoder_fetch.argtypes = [vp]
+            L.jb200_decoder_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+            L.jb200_decoder_last_timing.argtypes = [vp, D.F]
+            L.jb200_decoder_frame_counts.argtypes = [vp, C.c_int, D.I, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise Jb200Error(f"{what} failed ({rc}): {lib().jb200_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().jb200_launch_count())
+
+
+def _f(a):
+    return a.ctypes.data_as(D.F)
+
+
+class GmmScorer:
+    """All-state GMM scoring on the GPU (outprob_state/calc_mix/gprune_*/addlog_array/outprob_cd)."""
+
+    def __init__(self, ds: D.Descriptors, device: int = 0, mode: int = GMM_EXACT, gmm_desc=None):
+        self.ds = ds
+        self._h = C.c_void_p()
+        g = gmm_desc if gmm_desc is not None else ds.gmm
+        _check(lib().jb200_gmm_create(C.byref(g), device, mode, C.byref(self._h)), "jb200_gmm_create")
+        self.n_states = lib().jb200_gmm_n_states(self._h)
+        self.n_cdsets = lib().jb200_gmm_n_cdsets(self._h)
+        self.stride = lib().jb200_gmm_score_stride(self._h)
+        self.dim = g.dim
+
+    @property
+    def handle(self):
+        return self._h
+
+    def score(self, feats: np.ndarray) -> np.ndarray:
+        feats = np.ascontiguousarray(feats, np.float32)
+        T = feats.shape[0]
+        out = np.empty((T, self.n_states), np.float32)
+        _check(lib().jb200_gmm_score_host(self._h, _f(feats), T, _f(out)), "jb200_gmm_score_host")
+        return out
+
+    def score_rows(self, feats: np.ndarray) -> np.ndarray:
+        feats = np.ascontiguousarray(feats, np.float32)
+        T = feats.shape[0]
+        out = np.empty((T, self.stride), np.float32)
+        _check(lib().jb200_gmm_score_rows_host(self._h, _f(feats), T, _f(out)), "jb200_gmm_score_rows_host")
+        return out
+
+    def score_device(self, d_feats_ptr: int, T: int, d_rows_ptr: int, stream: int = 0):
+        _check(lib().jb200_gmm_score_device(self._h, d_feats_ptr, T, d_rows_ptr, stream or None), "jb200_gmm_score_device")
+
+    def gauss(self, feat: np.ndarray) -> np.ndarray:
+        feat = np.ascontiguousarray(feat, np.float32)
+        out = np.empty(self.ds.gmm.n_gauss, np.float32)
+        _check(lib().jb200_gmm_gauss_host(self._h, _f(feat), _f(out)), "jb200_gmm_gauss_host")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().jb200_gmm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Decoder:
+    """Batched pass-1 decoder (get_back_trellis_* / outprob_style / factoring lookups on the GPU)."""
+
+    def __init__(self, ds: D.Descriptors, am: GmmScorer, max_utts: int, max_frames: int):
+        self.ds, self.am = ds, am
+        self._h = C.c_void_p()
+        _check(lib().jb200_decoder_create(C.byref(ds.tree), am.handle, max_utts, max_frames, C.byref(self._h)),
+               "jb200_decoder_create")
+
+    @staticmethod
+    def _offsets(lengths):
+        off = np.zeros(len(lengths) + 1, np.int32)
+        np.cumsum(np.asarray(lengths, np.int64), out=off[1:])
+        return off
+
+    def decode(self, feats_list):
+        """feats_list: list of [T_u, dim] arrays (host).  Returns list of result dicts."""
+        off = self._offsets([len(x) for x in feats_list])
+        cat = np.ascontiguousarray(np.concatenate(feats_list, 0), np.float32)
+        _check(lib().jb200_decode_batch_host(self._h, _f(cat), off.ctypes.data_as(D.I), len(feats_list)),
+               "jb200_decode_batch_host")
+        return self.results()
+
+    def decode_scores(self, scores_list):
+        off = self._offsets([len(x) for x in scores_list])
+        cat = np.ascontiguousarray(np.concatenate(scores_list, 0), np.float32)
+        _check(lib().jb200_decode_batch_scores_host(self._h, _f(cat), off.ctypes.data_as(D.I), len(scores_list)),
+               "jb200_decode_batch_scores_host")
+        return self.results()
+
+    def decode_device(self, d_feats_ptr: int, frame_off: np.ndarray, fetch: bool = True):
+        frame_off = np.ascontiguousarray(frame_off, np.int32)
+        _check(lib().jb200_decode_batch_device(self._h, d_feats_ptr, frame_off.ctypes.data_as(D.I), len(frame_off) - 1),
+               "jb200_decode_batch_device")
+        if fetch:
+            _check(lib().jb200_decoder_fetch(self._h), "jb200_decoder_fetch")
+
+    def raw_results(self):
+        pu, pa, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().jb200_decoder_results(self._h, C.byref(pu), C.byref(pa), C.byref(pw)), "jb200_decoder_results")
+        return pu.value, pa.value, pw.value
+
+    def results(self, n_utts: int | None = None):
+        pu, pa, pw = self.raw_results()
+        n = self._last_n if n_utts is None else n_utts
+        utts = np.ctypeslib.as_array(C.cast(pu, C.POINTER(C.c_uint8)), shape=(n * UTT_DT.itemsize,)).view(UTT_DT)
+        out = []
+        for u in utts:
+            na, nw = int(u["n_atoms"]), int(u["n_words"])
+            atoms = np.ctypeslib.as_array(C.cast(pa + int(u["atom_offset"]) * ATOM_DT.itemsize, C.POINTER(C.c_uint8)),
+                                          shape=(max(na, 0) * ATOM_DT.itemsize,)).view(ATOM_DT).copy() if na > 0 else np.zeros(0, ATOM_DT)
+            words = np.ctypeslib.as_array(C.cast(pw + int(u["word_offset"]) * 4, D.I), shape=(nw,)).copy().tolist() if nw > 0 else []
+            out.append(dict(status=int(u["status"]), n_frames=int(u["n_frames"]), atoms=atoms, words=words,
+                            score=float(u["score"]), overflow=int(u["overflow"])))
+        return out
+
+    # the *_host entry points remember the batch size for results()
+    _last_n = 0
+
+    def timing(self):
+        ms = np.zeros(4, np.float32)
+        _check(lib().jb200_decoder_last_timing(self._h, _f(ms)), "jb200_decoder_last_timing")
+        return dict(h2d=float(ms[0]), score=float(ms[1]), beam=float(ms[2]), d2h=float(ms[3]))
+
+    def frame_counts(self, u: int, T: int):
+        c = np.zeros((T, 2), np.int32)
+        _check(lib().jb200_decoder_frame_counts(self._h, u, c.ctypes.data_as(D.I), T), "jb200_decoder_frame_counts")
+        return c
+
+    def close(self):
+        if self._h:
+            lib().jb200_decoder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,53 @@
+"""Regenerate the committed golden fixtures by running the UNMODIFIED compiled reference
+(oracle/_ref/jref, built by oracle/Makefile from /root/reference) on seeded synthetic models.
+
+    python tests/golden/make_golden.py
+
+Each fixture directory holds
+    model.jb2m  the reference's loaded models, flattened by the export plugin
+    out.jrf     reference outputs: [T x S] state scores, word trellis, pass-1 best
+    feats.npz   the input feature matrices (u0, u1, ...)
+    meta.json   the jconf-style options used
+"""
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from julius_b200 import synth  # noqa: E402
+from oracle import ffi, fixtures  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (preset, n_utts, n_frames, noise_utts, extra args)
+    "tiny": ("tiny", 2, 150, 0, []),
+    "small_b100": ("small", 2, 200, 1, ["-b", "100"]),
+    "small_safe": ("small", 1, 150, 0, ["-gprune", "safe", "-tmix", "2", "-b", "60", "-iwcd1", "max"]),
+}
+
+
+def main():
+    ffi.build()
+    for name, (preset, nu, nf, nn, extra) in CASES.items():
+        tmp = tempfile.mkdtemp(prefix="jb200_golden_")
+        m, files, dump, out = fixtures.make_fixture(preset, tmp, n_utts=nu, n_frames=nf, noise_utts=nn, extra_args=extra)
+        dst = os.path.join(HERE, name)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(tmp, "model.jb2m"), dst)
+        shutil.copy(dump, os.path.join(dst, "out.jrf"))
+        feats = {f"u{i}": synth.read_htk_param(fn)[0] for i, fn in enumerate(files)}
+        np.savez_compressed(os.path.join(dst, "feats.npz"), **feats)
+        with open(os.path.join(dst, "meta.json"), "w") as f:
+            json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "summary": out.strip().splitlines()[-1]}, f, indent=1)
+        shutil.rmtree(tmp)
+        print(name, "->", dst)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,46 @@
+"""CPU: the restatement (oracle/restate) must reproduce the compiled reference's outputs held
+in tests/golden bit for bit -- this is what pins the oracle (prompt section 3)."""
+import numpy as np
+import pytest
+
+from util import CASES, Golden, atoms_equal
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gmm_restatement_bit_exact(case, oracle_lib):
+    g = Golden(case)
+    for u, x in zip(g.utts, g.feats):
+        sc = oracle_lib.gmm_score(g.ds, x)
+        assert sc.shape == u.outprob.shape
+        assert np.array_equal(sc.view(np.uint32), u.outprob.view(np.uint32))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_beam_restatement_identical_trellis(case, oracle_lib):
+    g = Golden(case)
+    for u in g.utts:
+        r = oracle_lib.beam_decode(g.ds, u.outprob)
+        ok, why = atoms_equal(r["atoms"], u.atoms)
+        assert ok, why
+        assert r["status"] == u.status
+        assert r["words"] == u.words
+        assert np.float32(r["score"]) == np.float32(u.score)
+
+
+def test_addlog_table_matches_definition(oracle_lib):
+    t = oracle_lib.addlog_table()
+    i = np.array([0, 1, 1000, 250000, 499999])
+    f = -(np.float32(15) * i.astype(np.float32) / np.float32(500000))
+    want = np.log(1 + np.exp(f.astype(np.float64))).astype(np.float32)
+    assert np.array_equal(t[i], want)
+
+
+def test_cdset_scores_consistent_with_states(oracle_lib):
+    g = Golden("small_b100")
+    st = g.utts[0].outprob
+    cd = oracle_lib.cdset_score(g.ds, st)
+    off, ids = g.blob["am.cd_off"], g.blob["am.cd_states"]
+    # N-best average (N=3) of a set is bounded by its max and its mean of top-3 in float64
+    for c in range(0, cd.shape[1], 37):
+        v = np.sort(st[5, ids[off[c]:off[c + 1]]])[::-1][:3]
+        assert abs(cd[5, c] - v.astype(np.float64).mean()) < 1e-3

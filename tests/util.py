@@ -1,0 +1,42 @@
+import json
+import os
+
+import numpy as np
+
+from julius_b200 import desc, refdump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = ["tiny", "small_b100", "small_safe"]
+
+
+class Golden:
+    def __init__(self, name):
+        d = os.path.join(GOLDEN, name)
+        self.dir = d
+        self.blob = refdump.load_blob(os.path.join(d, "model.jb2m"))
+        self.ds = desc.Descriptors(self.blob)
+        self.utts = refdump.load_refdump(os.path.join(d, "out.jrf"))
+        z = np.load(os.path.join(d, "feats.npz"))
+        self.feats = [z[f"u{i}"] for i in range(len(self.utts))]
+        self.meta = json.load(open(os.path.join(d, "meta.json")))
+
+
+def atoms_equal(a, b):
+    """bit-exact comparison of two structured atom arrays (wid, begin, end, backscore, lscore, last)."""
+    if len(a) != len(b):
+        return False, f"atom count {len(a)} != {len(b)}"
+    for k in ("wid", "begin", "end", "last"):
+        if not np.array_equal(a[k], b[k]):
+            i = int(np.nonzero(a[k] != b[k])[0][0])
+            return False, f"field {k} differs first at atom {i}: {a[i]} vs {b[i]}"
+    for k in ("backscore", "lscore"):
+        if not np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)):
+            i = int(np.nonzero(a[k].view(np.uint32) != b[k].view(np.uint32))[0][0])
+            return False, f"field {k} differs (bits) first at atom {i}: {a[i]} vs {b[i]}"
+    return True, ""
+
+
+def rel_err(a, b, floor=1.0):
+    """|a-b| / max(|a|,|b|,floor): the relative criterion with an absolute floor (hard parts)."""
+    return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
