@@ -146,6 +146,7 @@ class Decoder:
         cat = np.ascontiguousarray(np.concatenate(feats_list, 0), np.float32)
         _check(lib().jb200_decode_batch_host(self._h, _f(cat), off.ctypes.data_as(D.I), len(feats_list)),
                "jb200_decode_batch_host")
+        self._last_n = len(feats_list)
         return self.results()
 
     def decode_scores(self, scores_list):
@@ -153,12 +154,14 @@ class Decoder:
         cat = np.ascontiguousarray(np.concatenate(scores_list, 0), np.float32)
         _check(lib().jb200_decode_batch_scores_host(self._h, _f(cat), off.ctypes.data_as(D.I), len(scores_list)),
                "jb200_decode_batch_scores_host")
+        self._last_n = len(scores_list)
         return self.results()
 
     def decode_device(self, d_feats_ptr: int, frame_off: np.ndarray, fetch: bool = True):
         frame_off = np.ascontiguousarray(frame_off, np.int32)
         _check(lib().jb200_decode_batch_device(self._h, d_feats_ptr, frame_off.ctypes.data_as(D.I), len(frame_off) - 1),
                "jb200_decode_batch_device")
+        self._last_n = len(frame_off) - 1
         if fetch:
             _check(lib().jb200_decoder_fetch(self._h), "jb200_decoder_fetch")
 

@@ -1,0 +1,1007 @@
+// beam.cu -- K3: pass-1 lexicon-tree token passing, one persistent thread block per utterance.
+//
+// Stands in for libjulius/src/beam.c get_back_trellis_init/_proceed/_end + finalize_1st_pass
+// (:1825, :2663, :3052, :3133), outprob_style (outprob_style.c:354-494), the factoring look-ups
+// (factoring_sub.c:942-1143, ngram_access.c:249-305) and the word-trellis store/sort
+// (backtrellis.c:190-267,438-478), for N-gram LMs, non-multipath HMMs, stock "fast" switches.
+//
+// Why this is not a transliteration.  The reference walks the survivors of frame t-1 one by one
+// and lets each arc "propagate" into a per-node slot; ties are won by whoever arrived first, new
+// tokens are numbered in order of first arrival, and the beam is cut by an in-place heap select
+// whose OUTPUT ORDER (it decides next frame's arrival order) depends on the heap's mechanics.
+// Scores sit on a coarse fp32 grid (|score| ~ 3e4 => ulp 2^-9), so exact ties are routine and
+// every one of these order effects is observable in the word trellis.  The kernel computes the
+// same fixed point with parallel primitives that are order-equivalent by construction:
+//   * every candidate transition gets the sequence number it would have had in the sequential
+//     walk:  seq = (survivor position j) * 2^18 + (arc index | n_intra + isolated-root index);
+//     the factoring pass gets j = n_survivors;
+//   * per destination node:  first arrival   = atomicMin(seq)          (who creates the token)
+//                            winning content = atomicMax(score, ~seq)  (strict '<' keeps the incumbent)
+//   * new-token numbering = rank of the creators' seq (bitonic sort in shared memory);
+//   * inter-word transitions into the "isolated" roots are pre-reduced per root over the frame's
+//     word-end tokens (max is associative; first/winner seqs are carried along); the per-last-word
+//     bigram rows the reference caches lazily (iw_sc_cache) are tabulated once at create time;
+//   * the beam cut replays the reference's heap select exactly: bottom-up heap construction is
+//     level-parallel (siftdowns of one level touch disjoint subtrees), the extractions are
+//     replayed by one thread on a shared-memory heap.
+// All frames of an utterance run inside one kernel launch; tokens, node slots and candidates
+// live in per-utterance global scratch (L2 resident), the sort/heap array in shared memory.
+//
+// Compiled with --fmad=false: every float decision uses the reference's fp32 expression order.
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+
+struct jb200_gmm;
+namespace jb200 {
+int gmm_device(const jb200_gmm *h);
+int gmm_dim(const jb200_gmm *h);
+int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st);
+int gmm_cd_device(const jb200_gmm *h, const int **cd_off, const int **cd_states, int *method, int *nbest);
+
+static constexpr int BEAM_THREADS = 256;
+static constexpr int NWARP = BEAM_THREADS / 32;
+static constexpr int SEQ_LOCAL_BITS = 18;
+static constexpr unsigned SEQ_LOCAL = 1u << SEQ_LOCAL_BITS;
+static constexpr int CD_NMAX = 16;
+static constexpr int MAX_WORDS = 150;      // MAXSEQNUM, libsent/include/sent/speech.h:50
+
+struct NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, scid; int out; int pad; };   // 32 B
+struct Tok { float score; int node; int tre; int cword; float lscore; int tre_wid; };              // 24 B
+struct Cand { float score; int node; float lscore; int src; };                                     // 16 B
+struct IsoCand { float score; int e; float lscore; int first_e; };                                 // 16 B
+struct WEnd { int j; int atom; int last_word; float base; int transp2; int nintra; };              // 24 B
+
+struct BeamParams {
+  // tree
+  const NodeRec *nodes; const int *arc_to; const float *arc_a;
+  const int *rset_ctx; const int *word_ctx; int n_ctx;
+  const int *iso_node; const int *iso_id; int n_iso; const float *iw;
+  const int *shared_node; const float *shared_f; int n_shared;
+  const float *wordend_a; const uint8_t *is_transp; const int *wton; const float *cprob;
+  const float *fscore; const int *scword;
+  const float *uni_prob; const float *uni_bow; const int *bi_bgn; const int *bi_num; const int *bi_wid; const float *bi_prob;
+  int lm_mode, lm_unk_id; float lm_unk_num_log;
+  float lm_weight, lm_penalty, lm_penalty_trans, prune_width;
+  int head_node, tail_silwid, beam, n_nodes;
+  // cd sets
+  const int *cd_off; const int *cd_states; int iwcd_method, iwcd_nbest;
+  // batch
+  const float *rows; int row_stride; const int *frame_off;
+  // per-utterance work areas (index = blockIdx.x)
+  Tok *tok; int *order; int *firstseq; unsigned long long *bestkey; Cand *cand; IsoCand *iso; WEnd *wend;
+  jb200_atom *atoms_raw; int *newidx; int *group0; int *counts;
+  const long long *atom_off;
+  // compact outputs
+  jb200_atom *atoms_out; unsigned long long *atom_counter; long long atoms_out_cap;
+  jb200_utt_result *results; int *words;
+  int maxt, maxc, maxw;
+};
+
+// ---- small device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned fkey(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ int search_bigram(const BeamParams &p, int wc, int w) {
+  int left = __ldg(p.bi_bgn + wc);
+  if (left < 0) return -1;
+  int right = left + __ldg(p.bi_num + wc) - 1;
+  while (left < right) {
+    int mid = (left + right) / 2;
+    if (__ldg(p.bi_wid + mid) < w) left = mid + 1; else right = mid;
+  }
+  return (__ldg(p.bi_wid + left) == w) ? left : -1;
+}
+
+// bi_prob_normal / _additional(_oldbin) / _compute, ngram_access.c:288-405
+__device__ float bigram_prob(const BeamParams &p, int w1, int w2) {
+  int n2; float prob;
+  if (p.lm_mode == JB200_BI_NORMAL || p.lm_mode == JB200_BI_ADDITIONAL_OLDBIN) {
+    if ((n2 = search_bigram(p, w1, w2)) >= 0) prob = __ldg(p.bi_prob + n2);
+    else prob = __ldg(p.uni_bow + w1) + __ldg(p.uni_prob + w2);
+  } else if (p.lm_mode == JB200_BI_ADDITIONAL) {
+    if ((n2 = search_bigram(p, w2, w1)) >= 0) prob = __ldg(p.bi_prob + n2);
+    else prob = __ldg(p.uni_bow + w1) + __ldg(p.uni_prob + w2);
+  } else {
+    if ((n2 = search_bigram(p, w2, w1)) >= 0) prob = __ldg(p.bi_prob + n2);
+    else prob = __ldg(p.uni_bow + w2) + __ldg(p.uni_prob + w1);
+    prob = prob + __ldg(p.uni_prob + w2) - __ldg(p.uni_prob + w1);
+  }
+  if (w2 != p.lm_unk_id) return prob;
+  return prob - p.lm_unk_num_log;
+}
+
+// max_successor_prob, factoring_sub.c:942-1012 (1-gram factoring build)
+__device__ __forceinline__ float max_successor_prob(const BeamParams &p, int lastword, int scid) {
+  if (lastword < 0) return 0.0f;
+  if (scid < 0) return __ldg(p.fscore - scid);
+  int w = __ldg(p.scword + scid);
+  return bigram_prob(p, __ldg(p.wton + lastword), __ldg(p.wton + w)) + __ldg(p.cprob + w);
+}
+
+// outprob_cd, outprob.c:286-400, evaluated on demand from the frame's state-score row
+__device__ float cdset_score(const BeamParams &p, const float *__restrict__ row, int c) {
+  const int b0 = __ldg(p.cd_off + c), n_in = __ldg(p.cd_off + c + 1) - b0;
+  if (p.iwcd_method == JB200_IWCD_AVG) {
+    float sum = 0.0f; int j = 0;
+    for (int i = 0; i < n_in; i++) { float v = __ldg(row + __ldg(p.cd_states + b0 + i)); if (v > JB200_LOG_ZERO) { sum += v; j++; } }
+    return sum / (float)j;
+  } else if (p.iwcd_method == JB200_IWCD_MAX) {
+    float mx = JB200_LOG_ZERO;
+    for (int i = 0; i < n_in; i++) { float v = __ldg(row + __ldg(p.cd_states + b0 + i)); if (mx < v) mx = v; }
+    return mx;
+  }
+  const int maxn = p.iwcd_nbest;
+  float mp[CD_NMAX + 1]; int n = 0;
+  for (int i = 0; i < n_in; i++) {
+    float prob = __ldg(row + __ldg(p.cd_states + b0 + i));
+    if (prob <= JB200_LOG_ZERO) continue;
+    if (n == 0 || prob <= mp[n - 1]) {
+      if (n == maxn) continue;
+      mp[n] = prob; n++;
+    } else {
+      for (int k = 0; k < n; k++) {
+        if (prob > mp[k]) {
+          int cnt = n - k - ((n == maxn) ? 1 : 0);
+          for (int q = k + cnt; q > k; q--) mp[q] = mp[q - 1];
+          mp[k] = prob;
+          break;
+        }
+      }
+      if (n < maxn) n++;
+    }
+  }
+  float prob = 0.0f;
+  for (int i = 0; i < n; i++) prob += mp[i];
+  return prob / (float)n;
+}
+
+// outprob_style, outprob_style.c:354-494 with the context resolution tabulated on the host
+__device__ __forceinline__ float outprob_style(const BeamParams &p, const float *__restrict__ row, int out, int last_wid) {
+  const int style = (unsigned)out >> 28, ref = out & 0x0fffffff;
+  if (style == JB200_AS_STATE) return __ldg(row + ref);
+  if (style == JB200_AS_LSET) return cdset_score(p, row, ref);
+  const int col = (last_wid < 0) ? p.n_ctx : __ldg(p.word_ctx + last_wid);
+  const int r = __ldg(p.rset_ctx + (size_t)ref * (p.n_ctx + 1) + col);
+  if (r >= 0) return __ldg(row + r);
+  return cdset_score(p, row, -r - 1);
+}
+
+// block-wide exclusive scan of one int per thread; *total = block sum.  Ends with a barrier.
+__device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int *total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int s = (lane < NWARP) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    if (lane < NWARP) warp_sums[lane] = s;   // inclusive
+  }
+  __syncthreads();
+  const int base = (wid == 0) ? 0 : warp_sums[wid - 1];
+  *total = warp_sums[NWARP - 1];
+  const int r = base + x - v;
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ void cand_atomics(int *firstseq, unsigned long long *bestkey,
+                                             int node, float score, unsigned seq_first, unsigned seq_win) {
+  atomicMin(firstseq + node, (int)seq_first);
+  unsigned long long key = ((unsigned long long)fkey(score) << 32) | (unsigned)(~seq_win);
+  atomicMax(bestkey + node, key);
+}
+
+// heap entries: high 32 bits = token id, low 32 bits = fp32 score bits.  1-based index h -> slot h-1.
+__device__ __forceinline__ float hval(unsigned long long e) { return __uint_as_float((unsigned)(e & 0xffffffffu)); }
+
+template <bool MAXHEAP>
+__device__ __forceinline__ void sift_down(unsigned long long *A, int start, int n) {
+  // the inner loop of sort_token_upward / _downward, beam.c:1355-1368 / :1421-1434
+  const unsigned long long s = A[start - 1];
+  const float sv = hval(s);
+  int parent = start, child;
+  while ((child = parent * 2) <= n) {
+    unsigned long long c = A[child - 1];
+    if (child < n) {
+      const unsigned long long c2 = A[child];
+      if (MAXHEAP ? (hval(c) < hval(c2)) : (hval(c) > hval(c2))) { child++; c = c2; }
+    }
+    if (MAXHEAP ? (sv >= hval(c)) : (sv <= hval(c))) break;
+    A[parent - 1] = c;
+    parent = child;
+  }
+  A[parent - 1] = s;
+}
+
+template <bool MAXHEAP>
+__device__ void heap_select(unsigned long long *A, int n, int extract) {
+  // build: roots n/2 .. 1; all roots of one tree level are independent (disjoint subtrees) and the
+  // sequential order visits deeper levels first, so a level-synchronous sweep is equivalent.
+  const int half = n >> 1;
+  if (half >= 1) {
+    for (int L = 31 - __clz(half); L >= 0; L--) {
+      const int lo = 1 << L;
+      const int hi = min((2 << L) - 1, half);
+      for (int i = lo + (int)threadIdx.x; i <= hi; i += BEAM_THREADS) sift_down<MAXHEAP>(A, i, n);
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    int m = n;
+    while (m > n - extract) {
+      const unsigned long long s = A[m - 1];
+      A[m - 1] = A[0];
+      m--;
+      if (m >= 1) {
+        // sift s down from the root of the shrunken heap (beam.c:1370-1384)
+        const float sv = hval(s);
+        int parent = 1, child;
+        while ((child = parent * 2) <= m) {
+          unsigned long long c = A[child - 1];
+          if (child < m) {
+            const unsigned long long c2 = A[child];
+            if (MAXHEAP ? (hval(c) < hval(c2)) : (hval(c) > hval(c2))) { child++; c = c2; }
+          }
+          if (MAXHEAP ? (sv >= hval(c)) : (sv <= hval(c))) break;
+          A[parent - 1] = c;
+          parent = child;
+        }
+        A[parent - 1] = s;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char beam_smem[];
+
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_kernel(const BeamParams p) {
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
+  const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
+
+  unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(beam_smem);   // [MAXT] sort keys, then heap entries
+  int *offs = reinterpret_cast<int *>(sbuf + MAXT);                               // [beam+2] candidate offsets per survivor
+  __shared__ int s_warp[NWARP + 1];
+  __shared__ int s_ncre, s_E, s_natoms, s_ns, s_cur, s_overflow, s_found;
+  __shared__ unsigned s_pmaxkey;
+  __shared__ unsigned long long s_webest;
+  __shared__ float s_thr;
+  __shared__ long long s_outbase;
+
+  Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
+  int *ord0 = p.order + (size_t)u * 2 * MAXT;
+  int *firstseq = p.firstseq + (size_t)u * p.n_nodes;
+  unsigned long long *bestkey = p.bestkey + (size_t)u * p.n_nodes;
+  Cand *cand = p.cand + (size_t)u * MAXC;
+  IsoCand *iso = p.iso + (size_t)u * max(p.n_iso, 1);
+  WEnd *wend = p.wend + (size_t)u * MAXW;
+  const long long a0 = p.atom_off[u];
+  const int atom_cap = (int)(p.atom_off[u + 1] - a0);
+  jb200_atom *araw = p.atoms_raw + a0;
+  int *newidx = p.newidx + a0;
+  int *group0 = p.group0 + (size_t)f_begin + u;          // [T+1]: first raw atom of end-frame group g
+  int *counts = p.counts + (size_t)f_begin * 2;
+  jb200_utt_result *res = p.results + u;
+  int *words = p.words + (size_t)u * MAX_WORDS;
+
+  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1; }
+  __syncthreads();
+
+  // ================= frame 0: init_nodescore (beam.c:1631-1665) + first sort (:1883) =================
+  if (T > 0 && tid == 0) {
+    const int node = p.head_node;
+    const NodeRec nr = p.nodes[node];
+    Tok tk;
+    float ll = (nr.scid != 0) ? max_successor_prob(p, -1, nr.scid) : 0.0f;
+    ll = ll * p.lm_weight + p.lm_penalty;
+    tk.lscore = ll; tk.tre = -1; tk.cword = -1; tk.tre_wid = -1; tk.node = node;
+    tk.score = outprob_style(p, p.rows + (size_t)f_begin * p.row_stride, nr.out, -1) + ll;
+    tok0[0] = tk;
+    ord0[0] = 0;
+    s_ns = 1;
+    counts[0] = 1; counts[1] = 1;
+  }
+  __syncthreads();
+
+  int tnum_prev = (T > 0) ? 1 : 0;      // tokens created in the previous frame (clear phase)
+  int groups = T;                       // number of end-frame groups kept by finalize (framelen)
+
+  // ================= frames 1..T-1: get_back_trellis_proceed (beam.c:2663-3019) =================
+  for (int t = 1; t < T; t++) {
+    const int cur = s_cur, nxt = cur ^ 1;
+    Tok *tl = tok0 + (size_t)cur * MAXT, *tn = tok0 + (size_t)nxt * MAXT;
+    int *ordl = ord0 + (size_t)cur * MAXT, *ordn = ord0 + (size_t)nxt * MAXT;
+    const int ns = s_ns;
+    const float thr = s_thr;
+    const float *row = p.rows + (size_t)(f_begin + t) * p.row_stride;
+
+    // ---- P0: clear_tokens (beam.c:1122): reset the node slots used by frame t-1
+    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+      const int node = tl[i].node;
+      __stcg(firstseq + node, 0x7fffffff);
+      __stcg(bestkey + node, 0ull);
+    }
+    if (tid == 0) { s_ncre = 0; s_webest = 0ull; s_pmaxkey = 0u; group0[t - 1] = s_natoms; }
+    __syncthreads();
+
+    // ---- P1: per survivor: candidate counts, word ends, trellis atoms (save_trellis, beam.c:2209)
+    int cand_total;
+    {
+      int carry_c = 0, carry_a = s_natoms, carry_w = 0;
+      for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
+        const int j = j0 + tid;
+        int nin = 0, is_we = 0, is_tr = 0;
+        Tok tk; NodeRec nr;
+        if (j < ns) {
+          tk = tl[ordl[j]];
+          nr = p.nodes[tk.node];
+          const bool valid = (tk.score > JB200_LOG_ZERO) && !(tk.score < thr);
+          if (valid) {
+            nin = (nr.self_a != JB200_LOG_ZERO) + (nr.next_a != JB200_LOG_ZERO) + nr.arc_n;
+            if (nr.stend >= 0) { is_we = 1; is_tr = (nr.stend != p.tail_silwid); }
+          }
+        }
+        int tot_c, tot_a, tot_w;
+        const int oc = block_excl_scan(nin, s_warp, &tot_c);
+        const int oa = block_excl_scan(is_we, s_warp, &tot_a);
+        const int ow = block_excl_scan(is_tr, s_warp, &tot_w);
+        if (j < ns) {
+          offs[j] = carry_c + oc;
+          if (is_we) {
+            const int ai = carry_a + oa;
+            if (ai < atom_cap) {
+              jb200_atom a;
+              a.wid = nr.stend; a.backscore = tk.score;
+              a.begintime = (tk.tre < 0 ? -1 : araw[tk.tre].endtime) + 1;
+              a.endtime = t - 1; a.last = tk.tre; a.lscore = tk.lscore;
+              araw[ai] = a;
+            } else s_overflow = 1;
+            if (is_tr) {
+              const int wi = carry_w + ow;
+              if (wi < MAXW && ai < atom_cap) {
+                WEnd w;
+                const int sword = nr.stend;
+                const int transp = p.is_transp[sword];
+                w.j = j; w.atom = ai; w.last_word = transp ? tk.cword : sword;
+                w.base = tk.score + __ldg(p.wordend_a + sword);
+                w.transp2 = (transp && tk.cword >= 0 && p.is_transp[tk.cword]) ? 1 : 0;
+                w.nintra = nin;
+                wend[wi] = w;
+                if (w.base > JB200_LOG_ZERO)   // beam.c:2308 keeps the FIRST maximum
+                  atomicMax(&s_webest, ((unsigned long long)fkey(w.base) << 32) | (unsigned)(~(unsigned)wi));
+              } else s_overflow = 1;
+            }
+          }
+        }
+        carry_c += tot_c; carry_a += tot_a; carry_w += tot_w;
+      }
+      cand_total = carry_c;
+      if (tid == 0) { offs[ns] = carry_c; s_natoms = min(carry_a, atom_cap); s_E = min(carry_w, MAXW); }
+      if (cand_total > MAXC) { if (tid == 0) s_overflow = 1; cand_total = 0; }
+    }
+    __syncthreads();
+    const int E = s_E;
+
+    // ---- P2a: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177)
+    if (cand_total > 0) {
+      for (int j = tid; j < ns; j += BEAM_THREADS) {
+        const int c0 = offs[j], nin = offs[j + 1] - c0;
+        if (nin == 0) continue;
+        const Tok tk = tl[ordl[j]];
+        const NodeRec nr = p.nodes[tk.node];
+        int k = 0;
+        for (int a = -2; a < nr.arc_n; a++) {
+          int next; float pa;
+          if (a == -2) { if (nr.self_a == JB200_LOG_ZERO) continue; next = tk.node; pa = nr.self_a; }
+          else if (a == -1) { if (nr.next_a == JB200_LOG_ZERO) continue; next = tk.node + 1; pa = nr.next_a; }
+          else { next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
+          float tmpsum = tk.score + pa;
+          float lsc = JB200_LOG_ZERO;
+          if (next != tk.node) {
+            const int scid = p.nodes[next].scid;
+            if (scid != 0) {
+              lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
+              tmpsum -= tk.lscore;
+              tmpsum += lsc;
+            }
+          }
+          if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
+          Cand c; c.score = tmpsum; c.node = next; c.lscore = lsc; c.src = j;
+          cand[c0 + k] = c;
+          if (tmpsum > JB200_LOG_ZERO) {
+            const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
+            cand_atomics(firstseq, bestkey, next, tmpsum, seq, seq);
+          }
+          k++;
+        }
+      }
+    }
+    // ---- P2b: cross-word transitions into isolated roots (beam_inter_word, beam.c:2271-2517),
+    //           pre-reduced per root over this frame's word ends, visited in survivor order
+    for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
+      const int col = __ldg(p.iso_id + i);
+      float best = JB200_LOG_ZERO, bestl = 0.0f; int beste = -1, firste = -1;
+      for (int e = 0; e < E; e++) {
+        const WEnd w = wend[e];
+        const float tmpprob = __ldg(p.iw + (size_t)w.last_word * p.n_iso + col);
+        const float lsc = tmpprob * p.lm_weight + p.lm_penalty;
+        float tmpsum = w.base;
+        tmpsum += lsc;
+        if (w.transp2) tmpsum += p.lm_penalty_trans;
+        if (tmpsum > JB200_LOG_ZERO) {
+          if (firste < 0) firste = e;
+          if (beste < 0 || best < tmpsum) { best = tmpsum; beste = e; bestl = lsc; }
+        }
+      }
+      IsoCand ic; ic.score = best; ic.e = beste; ic.lscore = bestl; ic.first_e = firste;
+      iso[i] = ic;
+      if (firste >= 0) {
+        const WEnd wf = wend[firste], wb = wend[beste];
+        const unsigned sf = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
+        const unsigned sw = (unsigned)wb.j * SEQ_LOCAL + (unsigned)(wb.nintra + i);
+        cand_atomics(firstseq, bestkey, __ldg(p.iso_node + i), best, sf, sw);
+      }
+    }
+    // ---- P2c: best word end -> shared (1-gram factored) roots (beam_inter_word_factoring, :2549-2616)
+    const unsigned long long webest = s_webest;
+    const bool have_we = (webest != 0ull);
+    WEnd wbest; wbest.base = 0.0f; wbest.atom = -1; wbest.last_word = -1; wbest.transp2 = 0; wbest.j = 0; wbest.nintra = 0;
+    if (have_we) {
+      wbest = wend[(unsigned)(~(unsigned)(webest & 0xffffffffu))];
+      for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
+        const float lsc = __ldg(p.shared_f + i) * p.lm_weight + p.lm_penalty;
+        float tmpsum = wbest.base;
+        tmpsum += lsc;
+        if (wbest.transp2) tmpsum += p.lm_penalty_trans;
+        if (tmpsum < thr) continue;
+        if (tmpsum > JB200_LOG_ZERO) {
+          const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
+          cand_atomics(firstseq, bestkey, __ldg(p.shared_node + i), tmpsum, seq, seq);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- P3: creators = candidates that were the first to reach their node
+    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
+      const Cand cd = cand[c];
+      if (!(cd.score > JB200_LOG_ZERO)) continue;
+      const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)(c - offs[cd.src]);
+      if ((unsigned)__ldcg(firstseq + cd.node) == seq) {
+        const int r = atomicAdd(&s_ncre, 1);
+        if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)cd.node;
+      }
+    }
+    for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
+      const IsoCand ic = iso[i];
+      if (ic.first_e < 0) continue;
+      const WEnd wf = wend[ic.first_e];
+      const unsigned seq = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
+      const int node = __ldg(p.iso_node + i);
+      if ((unsigned)__ldcg(firstseq + node) == seq) {
+        const int r = atomicAdd(&s_ncre, 1);
+        if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)node;
+      }
+    }
+    if (have_we) {
+      for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
+        const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
+        const int node = __ldg(p.shared_node + i);
+        if ((unsigned)__ldcg(firstseq + node) == seq) {
+          const int r = atomicAdd(&s_ncre, 1);
+          if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)node;
+        }
+      }
+    }
+    __syncthreads();
+    int ncre = s_ncre;
+    if (ncre > MAXT) { if (tid == 0) s_overflow = 1; ncre = MAXT; }
+
+    // ---- P4: creation order = ascending seq (create_token numbering, beam.c:1147-1162)
+    int npow = 1; while (npow < ncre) npow <<= 1;
+    for (int i = ncre + tid; i < npow; i += BEAM_THREADS) sbuf[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = tid; i < npow; i += BEAM_THREADS) {
+          const int ixj = i ^ jj;
+          if (ixj > i) {
+            const unsigned long long a = sbuf[i], b = sbuf[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { sbuf[i] = b; sbuf[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- P5: materialise tokens with the winner's content, add the output probability (beam.c:2944).
+    //          sbuf[r] is converted in place from sort key to heap entry (same thread reads then writes).
+    for (int r = tid; r < ncre; r += BEAM_THREADS) {
+      const int node = (int)(sbuf[r] & 0xffffffffu);
+      const unsigned long long bk = __ldcg(bestkey + node);
+      const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
+      const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
+      Tok nt; nt.node = node;
+      if (j == ns) {                                    // factoring pass
+        const float lsc = __ldg(p.shared_f + local) * p.lm_weight + p.lm_penalty;
+        float tmpsum = wbest.base; tmpsum += lsc;
+        if (wbest.transp2) tmpsum += p.lm_penalty_trans;
+        nt.score = tmpsum; nt.lscore = lsc; nt.tre = wbest.atom; nt.cword = wbest.last_word;
+        nt.tre_wid = araw[wbest.atom].wid;
+      } else {
+        const int c0 = offs[j], nin = offs[j + 1] - c0;
+        if (local < nin) {                              // word-internal candidate
+          const Cand cd = cand[c0 + local];
+          const Tok src = tl[ordl[j]];
+          nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = src.tre; nt.cword = src.cword; nt.tre_wid = src.tre_wid;
+        } else {                                        // isolated-root candidate
+          const IsoCand ic = iso[local - nin];
+          const WEnd w = wend[ic.e];
+          nt.score = ic.score; nt.lscore = ic.lscore; nt.tre = w.atom; nt.cword = w.last_word;
+          nt.tre_wid = araw[w.atom].wid;
+        }
+      }
+      nt.score += outprob_style(p, row, p.nodes[node].out, nt.tre_wid);
+      tn[r] = nt;
+      sbuf[r] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
+      if (p.prune_width >= 0.0f) atomicMax(&s_pmaxkey, fkey(nt.score));
+    }
+    __syncthreads();
+
+    // ---- P6: beam cut = the reference's heap select (sort_token_no_order, beam.c:1492-1520)
+    int ns_new, start;
+    {
+      const int need = p.beam, rest = ncre - need;
+      if (need >= ncre) { start = 0; ns_new = ncre; }
+      else if (need < rest) { heap_select<true>(sbuf, ncre, need); start = ncre - need; ns_new = need; }
+      else { heap_select<false>(sbuf, ncre, rest); start = 0; ns_new = need; }
+    }
+    for (int k = tid; k < ns_new; k += BEAM_THREADS) ordn[k] = (int)(sbuf[start + k] >> 32);
+    if (tid == 0) {
+      counts[2 * t] = ncre; counts[2 * t + 1] = ns_new;
+      s_ns = ns_new; s_cur = nxt;
+      if (p.prune_width >= 0.0f && s_pmaxkey != 0u) {
+        const unsigned k = s_pmaxkey;
+        const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+        s_thr = __uint_as_float(b) - p.prune_width;
+      } else s_thr = JB200_LOG_ZERO;
+    }
+    tnum_prev = ncre;
+    __syncthreads();
+    if (ncre == 0) { groups = t; break; }      // beam.c:3012-3015: no nodes left, search terminated
+  }
+
+  // ================= get_back_trellis_end (normal version, beam.c:3076-3086) =================
+  {
+    const int cur = s_cur;
+    Tok *tl = tok0 + (size_t)cur * MAXT;
+    int *ordl = ord0 + (size_t)cur * MAXT;
+    const int ns = (T > 0) ? s_ns : 0;
+    if (tid == 0 && T > 0 && groups == T) group0[T - 1] = s_natoms;
+    __syncthreads();
+    int carry_a = s_natoms;
+    for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
+      const int j = j0 + tid;
+      int is_we = 0; Tok tk; int stend = -1;
+      if (j < ns) { tk = tl[ordl[j]]; stend = p.nodes[tk.node].stend; is_we = (stend >= 0); }
+      int tot;
+      const int oa = block_excl_scan(is_we, s_warp, &tot);
+      if (is_we) {
+        const int ai = carry_a + oa;
+        if (ai < atom_cap) {
+          jb200_atom a;
+          a.wid = stend; a.backscore = tk.score;
+          a.begintime = (tk.tre < 0 ? -1 : araw[tk.tre].endtime) + 1;
+          a.endtime = T - 1; a.last = tk.tre; a.lscore = tk.lscore;     // save_trellis(t = samplenum)
+          araw[ai] = a;
+        } else s_overflow = 1;
+      }
+      carry_a += tot;
+    }
+    if (tid == 0) { s_natoms = min(carry_a, atom_cap); group0[groups] = s_natoms; }
+    // leave the node slots clean for the next utterance that uses this work area
+    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+      const int node = tl[i].node;
+      __stcg(firstseq + node, 0x7fffffff);
+      __stcg(bestkey + node, 0ull);
+    }
+    __syncthreads();
+  }
+
+  // ================= finalize_1st_pass: bt_relocate_rw + bt_sort_rw (backtrellis.c:218-267,438-478) ====
+  // group g = atoms with end frame g (raw atoms are grouped by creation frame already);
+  // inside a group order by word id (unique per group in this build: one token per node).
+  const int natoms = s_natoms;
+  for (int a = tid; a < natoms; a += BEAM_THREADS) {
+    const jb200_atom me = araw[a];
+    const int lo = group0[me.endtime], hi = group0[me.endtime + 1];
+    int rank = 0;
+    for (int b = lo; b < hi; b++) rank += (araw[b].wid < me.wid) ? 1 : 0;
+    newidx[a] = lo + rank;
+  }
+  if (tid == 0) {
+    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
+    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
+    else s_outbase = (long long)base;
+  }
+  __syncthreads();
+  const long long ob = s_outbase;
+  const bool can_write = (ob >= 0);
+  const int kept = can_write ? natoms : 0;
+  for (int a = tid; a < kept; a += BEAM_THREADS) {
+    jb200_atom me = araw[a];
+    me.last = (me.last < 0) ? -1 : newidx[me.last];
+    p.atoms_out[ob + newidx[a]] = me;
+    // find_1pass_result (beam.c:394-424): the latest end frame holding a </s> atom
+    if (me.wid == p.tail_silwid && me.backscore > JB200_LOG_ZERO) atomicMax(&s_found, me.endtime);
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  if (tid == 0) {
+    int status = 0, nw = 0; float score = 0.0f;
+    const int last_time = s_found;
+    if (kept == 0 || last_time < 0) status = -1;
+    else {
+      // the unique </s> atom of group last_time
+      const int lo = group0[last_time], hi = group0[last_time + 1];
+      int best = -1;
+      for (int b = lo; b < hi; b++) {
+        const jb200_atom x = p.atoms_out[ob + b];
+        if (x.wid == p.tail_silwid && x.backscore > JB200_LOG_ZERO) { best = b; break; }
+      }
+      if (best < 0) status = -1;
+      else {
+        // trace_backptr (beam.c:253-301)
+        int tmp[MAX_WORDS]; int n = 0; int a = best;
+        tmp[n++] = p.atoms_out[ob + a].wid;
+        while (p.atoms_out[ob + a].begintime > 0) {
+          a = p.atoms_out[ob + a].last;
+          if (a < 0 || n >= MAX_WORDS) break;
+          tmp[n++] = p.atoms_out[ob + a].wid;
+        }
+        for (int i = 0; i < n; i++) words[i] = tmp[n - i - 1];
+        nw = n; score = p.atoms_out[ob + best].backscore;
+      }
+    }
+    jb200_utt_result r;
+    r.status = status; r.n_frames = T; r.n_atoms = kept; r.n_words = nw; r.score = score;
+    r.atom_offset = ob; r.word_offset = u * MAX_WORDS; r.overflow = s_overflow;
+    *res = r;
+  }
+}
+
+// ---- set-up kernels ------------------------------------------------------------------------------
+__global__ void iw_table_kernel(BeamParams p, const int *iso_word, float *iw, int n_words) {
+  // max_successor_prob_iw (factoring_sub.c:1049-1143) for EVERY last word, once
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_words * p.n_iso) return;
+  const int lw = (int)(idx / p.n_iso), i = (int)(idx % p.n_iso);
+  const int w = iso_word[i];
+  iw[(size_t)lw * p.n_iso + p.iso_id[i]] = bigram_prob(p, p.wton[lw], p.wton[w]) + p.cprob[w];
+}
+
+__global__ void fill_slots_kernel(int *firstseq, unsigned long long *bestkey, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { firstseq[i] = 0x7fffffff; bestkey[i] = 0ull; }
+}
+
+}  // namespace jb200
+
+// =============================================================================================
+using namespace jb200;
+
+struct jb200_decoder {
+  jb200_gmm *am = nullptr;
+  int device = 0, dim = 0, S = 0, row_stride = 0;
+  int max_utts = 0, max_frames = 0;         // per batch: utterances, total frames
+  int atoms_per_frame = 64;
+  BeamParams P{};
+  std::vector<void *> dev_allocs;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5]{};
+  // batch buffers
+  float *d_feats = nullptr, *d_rows = nullptr;
+  int *d_frame_off = nullptr; long long *d_atom_off = nullptr;
+  jb200_atom *d_atoms_out = nullptr; unsigned long long *d_atom_counter = nullptr;
+  jb200_utt_result *d_results = nullptr; int *d_words = nullptr;
+  // host results (pinned)
+  jb200_utt_result *h_results = nullptr; jb200_atom *h_atoms = nullptr; int *h_words = nullptr;
+  unsigned long long *h_counter = nullptr;
+  long long atoms_cap = 0;
+  int last_n = 0; long long last_atoms = 0; int last_total_frames = 0;
+  std::vector<int> h_frame_off;
+  float last_ms[4] = {0, 0, 0, 0};
+  size_t smem_bytes = 0;
+  bool fetched = false;
+};
+
+template <typename Tp>
+static int dev_upload(jb200_decoder *d, const Tp *src, size_t n, const Tp **dst) {
+  Tp *p = nullptr;
+  JB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+  if (n) JB_CUDA(cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  d->dev_allocs.push_back(p);
+  *dst = p;
+  return JB200_OK;
+}
+template <typename Tp>
+static int dev_alloc(jb200_decoder *d, size_t n, Tp **dst) {
+  Tp *p = nullptr;
+  JB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+  d->dev_allocs.push_back(p);
+  *dst = p;
+  return JB200_OK;
+}
+
+extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  for (void *p : d->dev_allocs) cudaFree(p);
+  if (d->h_results) cudaFreeHost(d->h_results);
+  if (d->h_atoms) cudaFreeHost(d->h_atoms);
+  if (d->h_words) cudaFreeHost(d->h_words);
+  if (d->h_counter) cudaFreeHost(d->h_counter);
+  for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int max_utts, int max_frames, jb200_decoder **out) {
+  if (!t || !am || !out || max_utts < 1 || max_frames < 1) { set_error("jb200_decoder_create: bad argument"); return JB200_ERR_ARG; }
+  if (t->multipath) { set_error("multipath HMMs are not supported by the GPU beam yet"); return JB200_ERR_UNSUPPORTED; }
+  if (t->n_nodes >= (1 << 28)) { set_error("lexicon tree too large"); return JB200_ERR_UNSUPPORTED; }
+  if (t->beam_width < 1 || t->beam_width > 8000) { set_error("beam width %d outside 1..8000", t->beam_width); return JB200_ERR_UNSUPPORTED; }
+  jb200_decoder *d = new jb200_decoder();
+  d->am = am; d->device = gmm_device(am); d->dim = gmm_dim(am);
+  d->S = jb200_gmm_n_states(am);
+  d->row_stride = (d->S + 3) & ~3;
+  d->max_utts = max_utts; d->max_frames = max_frames;
+  if (const char *e = getenv("JB200_ATOMS_PER_FRAME")) d->atoms_per_frame = std::max(4, atoi(e));
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) { jb200_decoder_destroy(d); return rc; } } while (0)
+#define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_e)); jb200_decoder_destroy(d); return JB200_ERR_CUDA; } } while (0)
+  TRYC(cudaSetDevice(d->device));
+  TRYC(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  for (auto &e : d->ev) TRYC(cudaEventCreate(&e));
+
+  BeamParams &P = d->P;
+  const int n = t->n_nodes;
+  // node records
+  std::vector<NodeRec> nodes(n);
+  for (int i = 0; i < n; i++) {
+    NodeRec &r = nodes[i];
+    r.self_a = t->self_a[i]; r.next_a = t->next_a[i];
+    r.arc_off = t->arc_off[i]; r.arc_n = t->arc_off[i + 1] - t->arc_off[i];
+    r.stend = t->stend[i]; r.scid = t->scid[i];
+    const int style = t->outstyle[i];
+    if (style > 3) { set_error("non-emitting node in a non-multipath tree"); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
+    r.out = (int)(((unsigned)style << 28) | (unsigned)(t->out_ref[i] & 0x0fffffff));
+    r.pad = 0;
+  }
+  TRY(dev_upload(d, nodes.data(), nodes.size(), &P.nodes));
+  TRY(dev_upload(d, t->arc_to, (size_t)t->n_arcs, &P.arc_to));
+  TRY(dev_upload(d, t->arc_a, (size_t)t->n_arcs, &P.arc_a));
+  TRY(dev_upload(d, t->rset_ctx, (size_t)t->n_rset * (t->n_ctx + 1), &P.rset_ctx));
+  TRY(dev_upload(d, t->word_ctx, (size_t)t->n_words, &P.word_ctx));
+  P.n_ctx = t->n_ctx;
+  TRY(dev_upload(d, t->iso_node, (size_t)t->n_iso, &P.iso_node));
+  TRY(dev_upload(d, t->iso_id, (size_t)t->n_iso, &P.iso_id));
+  P.n_iso = t->n_iso;
+  TRY(dev_upload(d, t->shared_node, (size_t)t->n_shared, &P.shared_node));
+  {
+    std::vector<float> sf(std::max(t->n_shared, 1));
+    for (int i = 0; i < t->n_shared; i++) {
+      const int sc = t->scid[t->shared_node[i]];
+      if (sc >= 0) { set_error("shared root without 1-gram factoring value"); jb200_decoder_destroy(d); return JB200_ERR_ARG; }
+      sf[i] = t->fscore[-sc];
+    }
+    TRY(dev_upload(d, sf.data(), (size_t)t->n_shared, &P.shared_f));
+  }
+  P.n_shared = t->n_shared;
+  TRY(dev_upload(d, t->wordend_a, (size_t)t->n_words, &P.wordend_a));
+  TRY(dev_upload(d, t->is_transparent, (size_t)t->n_words, &P.is_transp));
+  TRY(dev_upload(d, t->wton, (size_t)t->n_words, &P.wton));
+  TRY(dev_upload(d, t->cprob, (size_t)t->n_words, &P.cprob));
+  TRY(dev_upload(d, t->fscore, (size_t)t->n_fscore, &P.fscore));
+  TRY(dev_upload(d, t->scword, (size_t)t->n_scword, &P.scword));
+  TRY(dev_upload(d, t->uni_prob, (size_t)t->lm_nvocab, &P.uni_prob));
+  TRY(dev_upload(d, t->uni_bow, (size_t)t->lm_nvocab, &P.uni_bow));
+  TRY(dev_upload(d, t->bi_bgn, (size_t)t->lm_nvocab, &P.bi_bgn));
+  TRY(dev_upload(d, t->bi_num, (size_t)t->lm_nvocab, &P.bi_num));
+  TRY(dev_upload(d, t->bi_wid, (size_t)t->lm_nbigram, &P.bi_wid));
+  TRY(dev_upload(d, t->bi_prob, (size_t)t->lm_nbigram, &P.bi_prob));
+  P.lm_mode = t->lm_mode; P.lm_unk_id = t->lm_unk_id; P.lm_unk_num_log = t->lm_unk_num_log;
+  P.lm_weight = t->lm_weight; P.lm_penalty = t->lm_penalty; P.lm_penalty_trans = t->lm_penalty_trans;
+  P.prune_width = t->score_pruning_width;
+  P.head_node = t->wordbegin[t->head_silwid]; P.tail_silwid = t->tail_silwid; P.beam = t->beam_width; P.n_nodes = n;
+  // cd sets come from the AM handle's descriptor: re-upload from the gmm handle is not exposed, so the
+  // decoder asks the scorer for its device copies
+  {
+    const int *co = nullptr, *cs = nullptr; int meth = 0, nb = 0;
+    gmm_cd_device(am, &co, &cs, &meth, &nb);
+    P.cd_off = co; P.cd_states = cs; P.iwcd_method = meth; P.iwcd_nbest = nb;
+  }
+  // inter-word bigram rows for every last word (the reference's iw_sc_cache, fully populated)
+  {
+    const int *d_iso_word = nullptr;
+    TRY(dev_upload(d, t->iso_word, (size_t)t->n_iso, &d_iso_word));
+    float *iw = nullptr;
+    TRY(dev_alloc(d, (size_t)t->n_words * std::max(t->n_iso, 1), &iw));
+    P.iw = iw;
+    const long long tot = (long long)t->n_words * t->n_iso;
+    if (tot > 0) {
+      iw_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P, d_iso_word, iw, t->n_words);
+      g_launches.fetch_add(1);
+      TRYC(cudaGetLastError());
+    }
+  }
+  // work areas
+  int maxt = 1; while (maxt < 2 * t->beam_width + t->n_start + 64) maxt <<= 1;
+  if (const char *e = getenv("JB200_MAXT")) { int v = atoi(e); maxt = 1; while (maxt < v) maxt <<= 1; }
+  P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
+  TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.tok));
+  TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.order));
+  TRY(dev_alloc(d, (size_t)max_utts * n, &P.firstseq));
+  TRY(dev_alloc(d, (size_t)max_utts * n, &P.bestkey));
+  TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.cand));
+  TRY(dev_alloc(d, (size_t)max_utts * std::max(t->n_iso, 1), &P.iso));
+  TRY(dev_alloc(d, (size_t)max_utts * P.maxw, &P.wend));
+  {
+    size_t tot = (size_t)max_utts * n;
+    fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.firstseq, P.bestkey, tot);
+    g_launches.fetch_add(1);
+    TRYC(cudaGetLastError());
+  }
+  d->atoms_cap = (long long)max_frames * d->atoms_per_frame + (long long)max_utts * 64;
+  TRY(dev_alloc(d, (size_t)d->atoms_cap, &P.atoms_raw));
+  TRY(dev_alloc(d, (size_t)d->atoms_cap, &P.newidx));
+  TRY(dev_alloc(d, (size_t)max_frames + max_utts + 8, &P.group0));
+  TRY(dev_alloc(d, (size_t)max_frames * 2 + 8, &P.counts));
+  TRY(dev_alloc(d, (size_t)d->atoms_cap, &d->d_atoms_out));
+  TRY(dev_alloc(d, 1, &d->d_atom_counter));
+  TRY(dev_alloc(d, (size_t)max_utts, &d->d_results));
+  TRY(dev_alloc(d, (size_t)max_utts * MAX_WORDS, &d->d_words));
+  TRY(dev_alloc(d, (size_t)max_utts + 1, &d->d_frame_off));
+  TRY(dev_alloc(d, (size_t)max_utts + 1, &d->d_atom_off));
+  TRY(dev_alloc(d, (size_t)max_frames * d->dim, &d->d_feats));
+  TRY(dev_alloc(d, (size_t)max_frames * d->row_stride, &d->d_rows));
+  TRYC(cudaMallocHost(&d->h_results, sizeof(jb200_utt_result) * max_utts));
+  TRYC(cudaMallocHost(&d->h_atoms, sizeof(jb200_atom) * (size_t)d->atoms_cap));
+  TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
+  TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
+  d->smem_bytes = (size_t)maxt * 8 + (size_t)(t->beam_width + 2) * 4;
+  TRYC(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
+  TRYC(cudaStreamSynchronize(d->stream));
+#undef TRY
+#undef TRYC
+  *out = d;
+  return JB200_OK;
+}
+
+static int prepare_batch(jb200_decoder *d, const int32_t *frame_off, int n_utts) {
+  if (!d || !frame_off || n_utts < 1) { set_error("decode: bad argument"); return JB200_ERR_ARG; }
+  if (n_utts > d->max_utts) { set_error("batch of %d utterances exceeds decoder capacity %d", n_utts, d->max_utts); return JB200_ERR_CAPACITY; }
+  const int total = frame_off[n_utts] - frame_off[0];
+  if (frame_off[0] != 0) { set_error("frame_off[0] must be 0"); return JB200_ERR_ARG; }
+  if (total > d->max_frames) { set_error("batch of %d frames exceeds decoder capacity %d", total, d->max_frames); return JB200_ERR_CAPACITY; }
+  std::vector<long long> aoff(n_utts + 1);
+  aoff[0] = 0;
+  for (int u = 0; u < n_utts; u++) {
+    const int T = frame_off[u + 1] - frame_off[u];
+    if (T < 0 || T > 32767) { set_error("utterance %d has %d frames (trellis times are 16-bit in the reference)", u, T); return JB200_ERR_ARG; }
+    aoff[u + 1] = aoff[u] + (long long)T * d->atoms_per_frame + 64;
+  }
+  JB_CUDA(cudaSetDevice(d->device));
+  d->h_frame_off.assign(frame_off, frame_off + n_utts + 1);
+  JB_CUDA(cudaMemcpyAsync(d->d_frame_off, frame_off, sizeof(int) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->d_atom_off, aoff.data(), sizeof(long long) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaMemsetAsync(d->d_atom_counter, 0, sizeof(unsigned long long), d->stream));
+  JB_CUDA(cudaStreamSynchronize(d->stream));   // aoff is a local
+  d->last_n = n_utts; d->last_total_frames = total; d->fetched = false;
+  return JB200_OK;
+}
+
+static int launch_beam(jb200_decoder *d, int n_utts) {
+  BeamParams P = d->P;
+  P.rows = d->d_rows; P.row_stride = d->row_stride; P.frame_off = d->d_frame_off;
+  P.atom_off = d->d_atom_off; P.atoms_out = d->d_atoms_out; P.atom_counter = d->d_atom_counter;
+  P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words;
+  beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
+  JB_LAUNCH_CHECK();
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_fetch(jb200_decoder *d) {
+  if (!d) { set_error("null decoder"); return JB200_ERR_ARG; }
+  if (d->fetched) return JB200_OK;
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaEventRecord(d->ev[3], d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->h_counter, d->d_atom_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->h_results, d->d_results, sizeof(jb200_utt_result) * d->last_n, cudaMemcpyDeviceToHost, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->h_words, d->d_words, sizeof(int) * (size_t)d->last_n * MAX_WORDS, cudaMemcpyDeviceToHost, d->stream));
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  long long na = (long long)*d->h_counter;
+  if (na > d->atoms_cap) na = d->atoms_cap;
+  d->last_atoms = na;
+  if (na > 0) JB_CUDA(cudaMemcpyAsync(d->h_atoms, d->d_atoms_out, sizeof(jb200_atom) * (size_t)na, cudaMemcpyDeviceToHost, d->stream));
+  JB_CUDA(cudaEventRecord(d->ev[4], d->stream));
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  cudaEventElapsedTime(&d->last_ms[0], d->ev[0], d->ev[1]);
+  cudaEventElapsedTime(&d->last_ms[1], d->ev[1], d->ev[2]);
+  cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
+  cudaEventElapsedTime(&d->last_ms[3], d->ev[3], d->ev[4]);
+  d->fetched = true;
+  return JB200_OK;
+}
+
+extern "C" int jb200_decode_batch_device(jb200_decoder *d, const float *d_feats, const int32_t *frame_off, int n_utts) {
+  int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
+  JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
+  rc = gmm_launch_states(d->am, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+  rc = launch_beam(d, n_utts); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[3], d->stream));
+  return JB200_OK;
+}
+
+extern "C" int jb200_decode_batch_host(jb200_decoder *d, const float *feats, const int32_t *frame_off, int n_utts) {
+  if (!feats) { set_error("null feats"); return JB200_ERR_ARG; }
+  int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->d_feats, feats, sizeof(float) * (size_t)d->last_total_frames * d->dim, cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
+  rc = gmm_launch_states(d->am, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+  rc = launch_beam(d, n_utts); if (rc) return rc;
+  return jb200_decoder_fetch(d);
+}
+
+extern "C" int jb200_decode_batch_scores_host(jb200_decoder *d, const float *scores, const int32_t *frame_off, int n_utts) {
+  if (!scores) { set_error("null scores"); return JB200_ERR_ARG; }
+  int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
+  JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
+  JB_CUDA(cudaMemcpy2DAsync(d->d_rows, sizeof(float) * d->row_stride, scores, sizeof(float) * d->S, sizeof(float) * d->S,
+                            d->last_total_frames, cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
+  JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+  rc = launch_beam(d, n_utts); if (rc) return rc;
+  return jb200_decoder_fetch(d);
+}
+
+extern "C" int jb200_decoder_results(jb200_decoder *d, const jb200_utt_result **utts, const jb200_atom **atoms, const int32_t **words) {
+  if (!d) { set_error("null decoder"); return JB200_ERR_ARG; }
+  if (!d->fetched) { int rc = jb200_decoder_fetch(d); if (rc) return rc; }
+  if (utts) *utts = d->h_results;
+  if (atoms) *atoms = d->h_atoms;
+  if (words) *words = d->h_words;
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_last_timing(jb200_decoder *d, float ms[4]) {
+  if (!d || !ms) { set_error("bad argument"); return JB200_ERR_ARG; }
+  for (int i = 0; i < 4; i++) ms[i] = d->last_ms[i];
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_frame_counts(jb200_decoder *d, int u, int32_t *counts, int max_frames) {
+  if (!d || !counts || u < 0 || u >= d->last_n) { set_error("bad argument"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  const int f0 = d->h_frame_off[u], T = d->h_frame_off[u + 1] - f0;
+  const int n = T < max_frames ? T : max_frames;
+  JB_CUDA(cudaMemcpy(counts, d->P.counts + (size_t)f0 * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost));
+  return JB200_OK;
+}

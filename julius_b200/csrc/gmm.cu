@@ -303,6 +303,10 @@ namespace jb200 {
 int gmm_device(const jb200_gmm *h) { return h->device; }
 cudaStream_t gmm_stream(const jb200_gmm *h) { return h->stream; }
 int gmm_dim(const jb200_gmm *h) { return h->D; }
+int gmm_cd_device(const jb200_gmm *h, const int **cd_off, const int **cd_states, int *method, int *nbest) {
+  *cd_off = h->d_cd_off; *cd_states = h->d_cd_states; *method = h->iwcd_method; *nbest = h->iwcd_nbest;
+  return 0;
+}
 }
 
 static void build_addlog_table(std::vector<float> &tbl) {
@@ -396,7 +400,7 @@ extern "C" int jb200_gmm_n_states(const jb200_gmm *h) { return h ? h->S : 0; }
 extern "C" int jb200_gmm_n_cdsets(const jb200_gmm *h) { return h ? h->C : 0; }
 
 template <int D>
-static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, cudaStream_t st) {
+static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st) {
   const int fblocks = (T + GMM_THREADS * GMM_FPT - 1) / (GMM_THREADS * GMM_FPT);
   // enough CTAs for >= 2 waves of 4 CTAs/SM when the frame count alone does not provide them
   int want = h->sm_count * 8;
@@ -408,7 +412,7 @@ static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, 
   dim3 grid(fblocks, chunks);
   const bool prune = h->gprune_method != JB200_GPRUNE_NONE;
   const bool exact = h->mode == JB200_GMM_EXACT;
-#define JB_GO(E, P) gmm_score_kernel<D, E, P><<<grid, GMM_THREADS, 0, st>>>(h->d_pk, h->d_tiles, tiles_per_chunk, h->n_tiles, d_feats, d_rows, T, h->row_stride, h->d_tbl, h->gprune_num)
+#define JB_GO(E, P) gmm_score_kernel<D, E, P><<<grid, GMM_THREADS, 0, st>>>(h->d_pk, h->d_tiles, tiles_per_chunk, h->n_tiles, d_feats, d_rows, T, row_stride, h->d_tbl, h->gprune_num)
   if (exact && !prune) JB_GO(true, false);
   else if (exact && prune) JB_GO(true, true);
   else if (!exact && !prune) JB_GO(false, false);
@@ -434,19 +438,26 @@ extern "C" int jb200_gmm_cdsets_device(jb200_gmm *h, float *d_rows, int T, void 
   return JB200_OK;
 }
 
+namespace jb200 {
+// state columns only, caller-chosen row stride (used by the decoder, which evaluates cd sets on demand)
+int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st) {
+  if (T <= 0) return JB200_OK;
+  JB_CUDA(cudaSetDevice(h->device));
+  switch (h->D) {
+    case 39: return launch_gmm<39>(h, d_feats, T, d_rows, row_stride, st);
+    case 38: return launch_gmm<38>(h, d_feats, T, d_rows, row_stride, st);
+    case 26: return launch_gmm<26>(h, d_feats, T, d_rows, row_stride, st);
+    case 25: return launch_gmm<25>(h, d_feats, T, d_rows, row_stride, st);
+    default: set_error("feature dimension %d not instantiated (39, 38, 26, 25)", h->D); return JB200_ERR_UNSUPPORTED;
+  }
+}
+}  // namespace jb200
+
 extern "C" int jb200_gmm_score_device(jb200_gmm *h, const float *d_feats, int T, float *d_rows, void *stream) {
   if (!h || !d_feats || !d_rows) { set_error("jb200_gmm_score_device: null argument"); return JB200_ERR_ARG; }
   if (T <= 0) return JB200_OK;
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  JB_CUDA(cudaSetDevice(h->device));
-  int rc;
-  switch (h->D) {
-    case 39: rc = launch_gmm<39>(h, d_feats, T, d_rows, st); break;
-    case 38: rc = launch_gmm<38>(h, d_feats, T, d_rows, st); break;
-    case 26: rc = launch_gmm<26>(h, d_feats, T, d_rows, st); break;
-    case 25: rc = launch_gmm<25>(h, d_feats, T, d_rows, st); break;
-    default: set_error("feature dimension %d not instantiated (39, 38, 26, 25)", h->D); return JB200_ERR_UNSUPPORTED;
-  }
+  int rc = gmm_launch_states(h, d_feats, T, d_rows, h->row_stride, st);
   if (rc) return rc;
   return jb200_gmm_cdsets_device(h, d_rows, T, st);
 }
