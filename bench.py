@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the acoustic-scoring + pass-1 beam hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload tri20k]
+    (N>1: launched by torch.distributed.run, one rank per GPU)
+
+A step = one pass of the hot path over one batch of synthetic utterances on every rank:
+    [H2D of the MFCC batch] -> K1 GMM state scoring -> K3 pass-1 beam -> [D2H of word trellis]
+`value`  : frames/s with the feature batch already resident in HBM, results left in HBM.
+`e2e`    : frames/s through the C-ABI call a host makes (jb200_decode_batch_host): pinned host
+           features in, word trellis + pass-1 best out, copies inside the timed region.
+`--impl reference` : the UNMODIFIED reference (oracle/_ref/jref, compiled from /root/reference by
+           oracle/Makefile) decoding the same workload on the host cores, as many processes as
+           there are cores; each step is a bounded sample.
+Utterances shard across ranks with no data-path collective (weak scaling: fixed batch per GPU);
+the only collective is the init-time NCCL broadcast of the flattened model from rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_GMM_BYTES_PER_GAUSS = 320          # (2D+2)*4 for D=39, streamed once per launch
+ALG_FLOPS_PER_GAUSS_FRAME = 162
+ALG_BEAM_BYTES_PER_TOKEN = 180         # SURVEY 8d per surviving token per frame
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="jb200", choices=["jb200", "reference"])
+    ap.add_argument("--workload", default="tri20k")
+    ap.add_argument("--utts", type=int, default=0, help="utterances per GPU per step (0 = one resident wave)")
+    ap.add_argument("--frames", type=int, default=1000, help="frames per utterance")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-utts", type=int, default=0)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.1 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference_sample(workload_name: str, n_procs: int, utts_per_proc: int, n_frames: int, seed: int):
+    """Decode utts_per_proc utterances in each of n_procs independent reference processes.
+    Returns (frames, seconds): seconds = the slowest process' time between PASS1_BEGIN and PASS1_END."""
+    from julius_b200 import synth, workload
+    jref = os.path.join(ROOT, "oracle", "_ref", "jref")
+    if not os.path.exists(jref):
+        raise RuntimeError("oracle/_ref/jref is missing (built by __graft_entry__.build() where /root/reference exists)")
+    m = workload.synth_model(workload_name)
+    tmp = tempfile.mkdtemp(prefix="jb200_ref_")
+    rng = np.random.default_rng(seed)
+    procs = []
+    env = dict(os.environ, JREF_QUIET="1")
+    for pi in range(n_procs):
+        files = []
+        for ui in range(utts_per_proc):
+            fn = os.path.join(tmp, f"p{pi}_u{ui}.mfc")
+            synth.write_htk_param(fn, m.sample_utterance(rng, n_frames)[0])
+            files.append(fn)
+        args = [jref, "-dump", os.path.join(tmp, f"p{pi}.jrf")] + workload.ref_args(workload_name)
+        p = subprocess.Popen(args, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+        p.stdin.write("\n".join(files) + "\n")
+        p.stdin.close()
+        procs.append(p)
+    secs, frames = [], 0
+    for p in procs:
+        out = p.stdout.read()
+        p.wait()
+        for line in out.splitlines():
+            if line.startswith("JREF_SUMMARY"):
+                kv = dict(x.split("=") for x in line.split()[1:])
+                secs.append(float(kv["decode_sec"])); frames += int(kv["frames"])
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    if not secs:
+        raise RuntimeError("reference produced no summary")
+    return frames, max(secs)
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores, 64))
+    upp = a.cpu_sample_utts or 2
+    # steps are bounded samples of the same workload
+    for w in range(min(a.warmup, 1)):
+        run_reference_sample(a.workload, n_procs, 1, min(a.frames, 200), 900 + w)
+    tot_f, tot_s = 0, 0.0
+    for k in range(a.steps):
+        f, s = run_reference_sample(a.workload, n_procs, upp, a.frames, 1000 + k)
+        tot_f += f; tot_s += s
+    v = tot_f / tot_s
+    line = {
+        "impl": "reference", "metric": "frames/sec (xRT) 20k-word triphone decode", "value": v, "unit": "frames/s",
+        "xRT": v / 100.0, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1000.0 * tot_s / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.workload}: tied-state triphone GMM 3000x16x39, 20k-word 2-gram, beam 800, -1pass; "
+                               f"{n_procs} independent reference processes x {upp} utterances x {a.frames} frames per step"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": n_procs, "kind": "reference",
+                         "sample": f"{a.steps} steps x {n_procs} procs x {upp} utts x {a.frames} frames; decode time between PASS1_BEGIN/END, max over processes"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------- product arm
+def broadcast_blob(blob, rank, world, device):
+    """Init-time NCCL broadcast of the flattened model from rank 0."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return blob
+    manifest = [None]
+    if rank == 0:
+        manifest[0] = [(k, str(v.dtype), int(v.size)) for k, v in blob.items()]
+    dist.broadcast_object_list(manifest, src=0)
+    total = sum(np.dtype(dt).itemsize * n + (-(np.dtype(dt).itemsize * n) % 16) for _, dt, n in manifest[0])
+    flat = torch.empty(total, dtype=torch.uint8, device=device)
+    if rank == 0:
+        host = np.zeros(total, np.uint8)
+        pos = 0
+        for k, dt, n in manifest[0]:
+            raw = blob[k].tobytes()
+            host[pos:pos + len(raw)] = np.frombuffer(raw, np.uint8)
+            pos += len(raw) + (-len(raw) % 16)
+        flat.copy_(torch.from_numpy(host))
+    dist.broadcast(flat, src=0)
+    host = flat.cpu().numpy()
+    out, pos = {}, 0
+    for k, dt, n in manifest[0]:
+        nb = np.dtype(dt).itemsize * n
+        out[k] = host[pos:pos + nb].view(dt).copy()
+        pos += nb + (-nb % 16)
+    return out
+
+
+def product_main(a):
+    import torch
+    import torch.distributed as dist
+    from julius_b200 import capi, desc, refdump, workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    if rank == 0 and not workload.ready(a.workload):
+        raise SystemExit(f"workload {a.workload} is not prepared (run __graft_entry__.build() where the reference is available)")
+    blob = refdump.load_blob(workload.path(a.workload, "model.jb2m")) if rank == 0 else None
+    blob = broadcast_blob(blob, rank, world, device)
+    ds = desc.Descriptors(blob)
+    S, M_total, D = ds.gmm.n_states, ds.gmm.n_gauss, ds.gmm.dim
+
+    am = capi.GmmScorer(ds, device=local, mode=capi.GMM_EXACT if a.mode == "exact" else capi.GMM_FAST)
+    T = a.frames
+    if a.utts:
+        B = a.utts
+    else:
+        probe = capi.Decoder(ds, am, max_utts=1, max_frames=8)
+        B = max(1, probe.resident_utts())      # one resident wave of thread blocks
+        probe.close()
+    dec = capi.Decoder(ds, am, max_utts=B, max_frames=B * T)
+
+    # synthetic MFCC batches sampled from the model along <s> w.. </s> paths, different per rank and step
+    m = workload.synth_model(a.workload)
+    n_batches = 2
+    off = np.arange(B + 1, dtype=np.int32) * T
+    host_batches, dev_batches = [], []
+    for bi in range(n_batches):
+        # a pool of 32 sampled utterances tiled to B (sampling 592k frames in numpy is the slow part)
+        pool = workload.sample_batch(m, min(B, 32), T, seed=100 + 17 * rank + bi)
+        feats = np.concatenate([pool[i % len(pool)] for i in range(B)], 0)
+        hb = torch.from_numpy(feats).pin_memory()
+        host_batches.append(hb)
+        dev_batches.append(hb.to(device))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = capi.lib()
+    offp = off.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def step_device(i):
+        db = dev_batches[i % n_batches]
+        capi._check(lib.jb200_decode_batch_device(dec.handle_ptr(), db.data_ptr(), offp, B), "decode_batch_device")
+
+    def step_host(i):
+        hb = host_batches[i % n_batches]
+        capi._check(lib.jb200_decode_batch_host(dec.handle_ptr(), C.cast(hb.data_ptr(), C.POINTER(C.c_float)), offp, B), "decode_batch_host")
+
+    # ---------------- value: device-resident input ----------------
+    for w in range(a.warmup):
+        step_device(w)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = capi.launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # events on the decoder's own stream are what the kernels run on; bracket with device-wide syncs
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    score_ms, beam_ms = [], []
+    for k in range(a.steps):
+        step_device(k)
+        capi._check(lib.jb200_decoder_sync_timing(dec.handle_ptr()), "sync_timing")
+        tm = dec.timing()
+        score_ms.append(tm["score"]); beam_ms.append(tm["beam"])
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    t_wall1 = time.time()
+    launches = capi.launch_count() - l0
+    dev_ms = sum(score_ms) + sum(beam_ms)          # CUDA-event time on the launching stream
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---------------- e2e: host buffers through the C-ABI ----------------
+    for w in range(max(1, min(a.warmup, 2))):
+        step_host(w)
+    barrier()
+    t2 = time.perf_counter()
+    h2d = d2h = 0
+    for k in range(a.steps):
+        step_host(k)
+        h2d += host_batches[k % n_batches].numel() * 4
+        res_bytes = dec.last_d2h_bytes()
+        d2h += res_bytes
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    barrier()
+
+    # sanity: results of the last batch are sane (all utterances decoded, no overflow)
+    res = dec.results()
+    n_ok = sum(1 for r in res if r["status"] == 0 and r["overflow"] == 0)
+    counts = dec.frame_counts(0, T)
+
+    # max over ranks
+    vals = torch.tensor([dev_ms, (t1 - t0) * 1000.0, (t3 - t2) * 1000.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in vals.cpu()]
+
+    if rank == 0:
+        frames_total = world * B * T * a.steps
+        value = frames_total / (wall_ms_max / 1000.0)
+        e2e = frames_total / (e2e_ms_max / 1000.0)
+        peak, peak_src = peaks()
+        gmm_ms = float(np.mean(score_ms)); bm_ms = float(np.mean(beam_ms))
+        tokens_per_frame = float(counts[:, 1].mean())
+        created_per_frame = float(counts[:, 0].mean())
+        gmm_bytes = M_total * ALG_GMM_BYTES_PER_GAUSS + B * T * (D * 4 + 4 * S)
+        beam_bytes = B * T * tokens_per_frame * ALG_BEAM_BYTES_PER_TOKEN
+        if bm_ms >= gmm_ms:
+            dom, dom_ms, dom_bytes = "beam_kernel", bm_ms, beam_bytes
+        else:
+            dom, dom_ms, dom_bytes = "gmm_score_kernel", gmm_ms, gmm_bytes
+        ach = dom_bytes / (dom_ms / 1000.0) / 1e9
+        line = {
+            "metric": "frames/sec (xRT) 20k-word triphone decode", "value": value, "unit": "frames/s", "xRT": value / 100.0,
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall_ms_max / a.steps, "device_event_ms_per_step": dev_ms_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{a.workload}: tied-state triphone GMM {S} states x 16 mix x {D} dim, 20k-word 2-gram "
+                                   f"(BASELINE configs[1]), beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
+                                   f"GMM arithmetic mode {a.mode}",
+                       "utts_per_gpu": B, "frames_per_utt": T,
+                       "l2": "per-step working set (score matrix %.1f GB) exceeds L2; input batch alternates" % (B * T * S * 4 / 1e9),
+                       "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": {"gmm_score_kernel": gmm_ms, "beam_kernel": bm_ms},
+                         "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
+                         "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
+                         "beam_tokens_per_frame": tokens_per_frame, "beam_created_per_frame": created_per_frame},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
+                    "ms_per_step": e2e_ms_max / a.steps},
+            "gpu_launches": int(launches),
+            "decoded_ok": f"{n_ok}/{len(res)}", "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                n_procs = max(1, min(cores, 64))
+                upp = a.cpu_sample_utts or 2
+                f, s = run_reference_sample(a.workload, n_procs, upp, T, 4242)
+                line["cpu_baseline"] = {"value": f / s, "unit": "frames/s", "cores": n_procs, "kind": "reference",
+                                        "sample": f"{n_procs} reference processes x {upp} utterances x {T} frames of the same workload; "
+                                                  f"decode time between PASS1_BEGIN/END, max over processes ({s:.1f} s)"}
+            except Exception as e:   # the bench line must still print
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(reference_main(args) if args.impl == "reference" else product_main(args))

@@ -125,6 +125,12 @@ int jb200_decoder_results(jb200_decoder *d, const jb200_utt_result **utts, const
 /* timing of the last batch in milliseconds (CUDA events on the decoder's stream):
  * [0]=H2D, [1]=acoustic scoring, [2]=beam, [3]=D2H */
 int jb200_decoder_last_timing(jb200_decoder *d, float ms[4]);
+/* wait for the last batch's kernels and refresh the timing (device variant, no D2H) */
+int jb200_decoder_sync_timing(jb200_decoder *d);
+/* bytes moved device->host by the last fetch (results + atoms + words) */
+int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d);
+/* how many utterances (thread blocks) are co-resident on the device for this decoder */
+int jb200_decoder_resident_utts(const jb200_decoder *d);
 /* per-frame token counts of utterance u of the last batch (debug / roofline accounting):
  * counts [T][2] = (tokens created, survivors) */
 int jb200_decoder_frame_counts(jb200_decoder *d, int u, int32_t *counts, int max_frames);

@@ -56,6 +56,10 @@ def lib():
             L.jb200_decoder_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
             L.jb200_decoder_last_timing.argtypes = [vp, D.F]
             L.jb200_decoder_frame_counts.argtypes = [vp, C.c_int, D.I, C.c_int]
+            L.jb200_decoder_sync_timing.argtypes = [vp]
+            L.jb200_decoder_last_d2h_bytes.argtypes = [vp]
+            L.jb200_decoder_last_d2h_bytes.restype = C.c_int64
+            L.jb200_decoder_resident_utts.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -186,6 +190,15 @@ class Decoder:
 
     # the *_host entry points remember the batch size for results()
     _last_n = 0
+
+    def handle_ptr(self):
+        return self._h
+
+    def last_d2h_bytes(self) -> int:
+        return int(lib().jb200_decoder_last_d2h_bytes(self._h))
+
+    def resident_utts(self) -> int:
+        return int(lib().jb200_decoder_resident_utts(self._h))
 
     def timing(self):
         ms = np.zeros(4, np.float32)

@@ -726,6 +726,8 @@ struct jb200_decoder {
   float last_ms[4] = {0, 0, 0, 0};
   size_t smem_bytes = 0;
   bool fetched = false;
+  long long last_d2h = 0;
+  int resident = 0;
 };
 
 template <typename Tp>
@@ -884,6 +886,12 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
   d->smem_bytes = (size_t)maxt * 8 + (size_t)(t->beam_width + 2) * 4;
   TRYC(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
+  {
+    int per_sm = 0, sms = 0;
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, BEAM_THREADS, d->smem_bytes));
+    TRYC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
+    d->resident = per_sm * sms;
+  }
   TRYC(cudaStreamSynchronize(d->stream));
 #undef TRY
 #undef TRYC
@@ -943,9 +951,25 @@ extern "C" int jb200_decoder_fetch(jb200_decoder *d) {
   cudaEventElapsedTime(&d->last_ms[1], d->ev[1], d->ev[2]);
   cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
   cudaEventElapsedTime(&d->last_ms[3], d->ev[3], d->ev[4]);
+  d->last_d2h = (long long)sizeof(unsigned long long) + (long long)sizeof(jb200_utt_result) * d->last_n +
+                (long long)sizeof(int) * d->last_n * MAX_WORDS + (long long)sizeof(jb200_atom) * na;
   d->fetched = true;
   return JB200_OK;
 }
+
+extern "C" int jb200_decoder_sync_timing(jb200_decoder *d) {
+  if (!d) { set_error("null decoder"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaEventSynchronize(d->ev[3]));
+  cudaEventElapsedTime(&d->last_ms[0], d->ev[0], d->ev[1]);
+  cudaEventElapsedTime(&d->last_ms[1], d->ev[1], d->ev[2]);
+  cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
+  d->last_ms[3] = 0.0f;
+  return JB200_OK;
+}
+
+extern "C" int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d) { return d ? d->last_d2h : 0; }
+extern "C" int jb200_decoder_resident_utts(const jb200_decoder *d) { return d ? d->resident : 0; }
 
 extern "C" int jb200_decode_batch_device(jb200_decoder *d, const float *d_feats, const int32_t *frame_off, int n_utts) {
   int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;

@@ -1,0 +1,85 @@
+"""GPU, BASELINE.json full size (3000 states x 16 mix x 39, 20k-word tree, beam 800): the CUDA path
+vs the CPU restatement on the same seeded inputs, plus size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from julius_b200 import capi, desc, refdump, workload
+from util import atoms_equal
+
+pytestmark = pytest.mark.gpu
+
+NAME = "tri20k"
+
+
+@pytest.fixture(scope="module")
+def full():
+    if not workload.ready(NAME):
+        pytest.skip("workloads/tri20k not prepared (built by __graft_entry__.build())")
+    blob = refdump.load_blob(workload.path(NAME, "model.jb2m"))
+    ds = desc.Descriptors(blob)
+    m = workload.synth_model(NAME)
+    am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(ds, am, max_utts=16, max_frames=16 * 400)
+    return dict(blob=blob, ds=ds, m=m, am=am, dec=dec)
+
+
+def test_full_size_gmm_bit_exact_vs_oracle(full, oracle_lib):
+    x = workload.sample_batch(full["m"], 1, 64, seed=7)[0]
+    got = full["am"].score(x)
+    want = oracle_lib.gmm_score(full["ds"], x)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_full_size_end_to_end_vs_oracle(full, oracle_lib):
+    """host MFCC -> GPU scoring -> GPU beam == oracle scoring -> oracle beam, atom for atom."""
+    feats = workload.sample_batch(full["m"], 3, 300, seed=21)
+    feats.append(full["m"].sample_noise(np.random.default_rng(5), 120))      # worst-case beam
+    res = full["dec"].decode(feats)
+    for x, r in zip(feats, res):
+        sc = oracle_lib.gmm_score(full["ds"], x)
+        o = oracle_lib.beam_decode(full["ds"], sc)
+        assert r["overflow"] == 0
+        ok, why = atoms_equal(r["atoms"], o["atoms"])
+        assert ok, why
+        assert r["words"] == o["words"] and r["status"] == o["status"]
+
+
+def test_probe_utterance_matches_compiled_reference(full):
+    """workloads/tri20k/probe.* was decoded by the compiled reference when the workload was built."""
+    u = refdump.load_refdump(workload.path(NAME, "probe.jrf"))[0]
+    from julius_b200 import synth
+    x, _ = synth.read_htk_param(workload.path(NAME, "probe.mfc"))
+    r = full["dec"].decode([x])[0]
+    ok, why = atoms_equal(r["atoms"], u.atoms)
+    assert ok, why
+    assert r["words"] == u.words and np.float32(r["score"]) == np.float32(u.score)
+
+
+def test_trellis_structure_properties_at_full_batch(full):
+    """Size-independent invariants on a larger batch: times are ordered, back pointers point to
+    earlier atoms whose end frame precedes the begin frame, atoms are frame-major / wid-sorted,
+    the best path ends in </s> at the last frame and starts with <s>."""
+    feats = workload.sample_batch(full["m"], 16, 400, seed=33)
+    res = full["dec"].decode(feats)
+    tail, head = full["ds"].tree.tail_silwid, full["ds"].tree.head_silwid
+    for r in res:
+        a = r["atoms"]
+        assert r["status"] == 0 and r["overflow"] == 0 and len(a) > 0
+        key = a["end"].astype(np.int64) * 100000 + a["wid"]
+        assert np.all(np.diff(key) > 0)
+        assert np.all(a["begin"] <= a["end"] + 1)
+        has = a["last"] >= 0
+        assert np.all(a["last"][has] < np.nonzero(has)[0])
+        assert np.all(a["end"][a["last"][has]] + 1 == a["begin"][has])
+        assert np.all(a["begin"][~has] == 0)
+        assert r["words"][0] == head and r["words"][-1] == tail
+
+
+def test_fast_mode_scores_within_tolerance_and_decodes(full):
+    am = capi.GmmScorer(full["ds"], mode=capi.GMM_FAST)
+    x = workload.sample_batch(full["m"], 1, 128, seed=9)[0]
+    a, b = am.score(x), full["am"].score(x)
+    rel = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)
+    assert rel.max() <= 1e-4      # BASELINE.json north_star tolerance on float log-likelihoods
