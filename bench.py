@@ -316,7 +316,9 @@ def product_main(a):
     barrier()
 
     # sanity: results of the last batch are sane (all utterances decoded, no overflow)
+    dec._last_n = B
     res = dec.results()
+    phase = dec.phase_cycles(min(B, 64)).mean(0)
     n_ok = sum(1 for r in res if r["status"] == 0 and r["overflow"] == 0)
     counts = dec.frame_counts(0, T)
 
@@ -356,11 +358,12 @@ def product_main(a):
                          "kernel_ms": {"gmm_score_kernel": gmm_ms, "beam_kernel": bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
                          "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
+                         "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_select", "rest"), phase)},
                          "beam_tokens_per_frame": tokens_per_frame, "beam_created_per_frame": created_per_frame},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                     "ms_per_step": e2e_ms_max / a.steps},
             "gpu_launches": int(launches),
-            "decoded_ok": f"{n_ok}/{len(res)}", "clocks": clocks,
+            "decoded_ok": f"{n_ok}/{len(res)}", "heap_misspeculations": dec.misspeculations(), "clocks": clocks,
         }
         if world == 1 and not a.no_cpu_baseline:
             try:

@@ -129,8 +129,13 @@ int jb200_decoder_last_timing(jb200_decoder *d, float ms[4]);
 int jb200_decoder_sync_timing(jb200_decoder *d);
 /* bytes moved device->host by the last fetch (results + atoms + words) */
 int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d);
+/* how often (frames, since create) the pipelined heap replay had to fall back to the sequential one */
+int64_t jb200_decoder_misspeculations(jb200_decoder *d);
 /* how many utterances (thread blocks) are co-resident on the device for this decoder */
 int jb200_decoder_resident_utts(const jb200_decoder *d);
+/* SM-cycle totals per kernel phase of the first n_utts utterances of the last batch: cycles [n_utts][8]
+ * 0 clear, 1 count/atoms, 2 expand, 3 creators, 4 order sort, 5 materialise+outprob, 6 heap select, 7 rest */
+int jb200_decoder_phase_cycles(jb200_decoder *d, int64_t *cycles, int n_utts);
 /* per-frame token counts of utterance u of the last batch (debug / roofline accounting):
  * counts [T][2] = (tokens created, survivors) */
 int jb200_decoder_frame_counts(jb200_decoder *d, int u, int32_t *counts, int max_frames);

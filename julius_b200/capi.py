@@ -60,6 +60,9 @@ def lib():
             L.jb200_decoder_last_d2h_bytes.argtypes = [vp]
             L.jb200_decoder_last_d2h_bytes.restype = C.c_int64
             L.jb200_decoder_resident_utts.argtypes = [vp]
+            L.jb200_decoder_misspeculations.argtypes = [vp]
+            L.jb200_decoder_misspeculations.restype = C.c_int64
+            L.jb200_decoder_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
         _lib = L
     return _lib
 
@@ -197,8 +200,16 @@ class Decoder:
     def last_d2h_bytes(self) -> int:
         return int(lib().jb200_decoder_last_d2h_bytes(self._h))
 
+    def misspeculations(self) -> int:
+        return int(lib().jb200_decoder_misspeculations(self._h))
+
     def resident_utts(self) -> int:
         return int(lib().jb200_decoder_resident_utts(self._h))
+
+    def phase_cycles(self, n_utts: int) -> np.ndarray:
+        c = np.zeros((n_utts, 8), np.int64)
+        _check(lib().jb200_decoder_phase_cycles(self._h, c.ctypes.data_as(C.POINTER(C.c_int64)), n_utts), "jb200_decoder_phase_cycles")
+        return c
 
     def timing(self):
         ms = np.zeros(4, np.float32)

@@ -39,7 +39,10 @@ int gmm_dim(const jb200_gmm *h);
 int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st);
 int gmm_cd_device(const jb200_gmm *h, const int **cd_off, const int **cd_states, int *method, int *nbest);
 
-static constexpr int BEAM_THREADS = 256;
+#ifndef JB200_BEAM_THREADS
+#define JB200_BEAM_THREADS 256
+#endif
+static constexpr int BEAM_THREADS = JB200_BEAM_THREADS;
 static constexpr int NWARP = BEAM_THREADS / 32;
 static constexpr int SEQ_LOCAL_BITS = 18;
 static constexpr unsigned SEQ_LOCAL = 1u << SEQ_LOCAL_BITS;
@@ -75,7 +78,11 @@ struct BeamParams {
   // compact outputs
   jb200_atom *atoms_out; unsigned long long *atom_counter; long long atoms_out_cap;
   jb200_utt_result *results; int *words;
-  int maxt, maxc, maxw;
+  long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
+  unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
+  unsigned long long *outv;          // per-utterance extracted heap roots [beam+1]
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap;
+  int maxt, maxc, maxw, maxbits;
 };
 
 // ---- small device helpers ----------------------------------------------------------------------
@@ -198,30 +205,67 @@ __device__ __forceinline__ void cand_atomics(int *firstseq, unsigned long long *
   atomicMax(bestkey + node, key);
 }
 
-// heap entries: high 32 bits = token id, low 32 bits = fp32 score bits.  1-based index h -> slot h-1.
+// heap entries: high 32 bits = token id, low 32 bits = fp32 score bits.  Heap index h (1-based) lives
+// in slot h, so the sibling pair (2p, 2p+1) is one aligned 16-byte word.
 __device__ __forceinline__ float hval(unsigned long long e) { return __uint_as_float((unsigned)(e & 0xffffffffu)); }
+
+template <bool MAXHEAP>
+__device__ __forceinline__ bool hcmp(float a, float b) { return MAXHEAP ? (a < b) : (a > b); }      // "child < child+1"
+template <bool MAXHEAP>
+__device__ __forceinline__ bool hstop(float s, float c) { return MAXHEAP ? (s >= c) : (s <= c); }   // "STVAL >= SVAL(child)"
 
 template <bool MAXHEAP>
 __device__ __forceinline__ void sift_down(unsigned long long *A, int start, int n) {
   // the inner loop of sort_token_upward / _downward, beam.c:1355-1368 / :1421-1434
-  const unsigned long long s = A[start - 1];
+  const unsigned long long s = A[start];
   const float sv = hval(s);
   int parent = start, child;
   while ((child = parent * 2) <= n) {
-    unsigned long long c = A[child - 1];
-    if (child < n) {
-      const unsigned long long c2 = A[child];
-      if (MAXHEAP ? (hval(c) < hval(c2)) : (hval(c) > hval(c2))) { child++; c = c2; }
-    }
-    if (MAXHEAP ? (sv >= hval(c)) : (sv <= hval(c))) break;
-    A[parent - 1] = c;
+    const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(A + child);
+    unsigned long long c = pr.x;
+    if (child < n && hcmp<MAXHEAP>(hval(pr.x), hval(pr.y))) { child++; c = pr.y; }
+    if (hstop<MAXHEAP>(sv, hval(c))) break;
+    A[parent] = c;
     parent = child;
   }
-  A[parent - 1] = s;
+  A[parent] = s;
+}
+
+// one extraction step chain, two tree levels per shared-memory round trip
+template <bool MAXHEAP>
+__device__ __forceinline__ void sift_root_2level(unsigned long long *A, const unsigned long long s, const int m) {
+  const float sv = hval(s);
+  int parent = 1;
+  while (true) {
+    int child = parent * 2;
+    if (child > m) break;
+    // children pair and the four grandchildren (slots 4p..4p+3), loaded together
+    const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(A + child);
+    const int g = parent * 4;
+    ulonglong2 g01 = make_ulonglong2(0ull, 0ull), g23 = make_ulonglong2(0ull, 0ull);
+    if (g <= m) g01 = *reinterpret_cast<const ulonglong2 *>(A + g);
+    if (g + 2 <= m) g23 = *reinterpret_cast<const ulonglong2 *>(A + g + 2);
+    // level 1
+    unsigned long long c = pr.x; bool right = false;
+    if (child < m && hcmp<MAXHEAP>(hval(pr.x), hval(pr.y))) { right = true; c = pr.y; }
+    if (hstop<MAXHEAP>(sv, hval(c))) break;
+    A[parent] = c;
+    parent = child + (right ? 1 : 0);
+    // level 2 (children of the chosen child are g01 or g23)
+    child = parent * 2;
+    if (child > m) break;
+    const ulonglong2 q = right ? g23 : g01;
+    unsigned long long c2 = q.x; bool right2 = false;
+    if (child < m && hcmp<MAXHEAP>(hval(q.x), hval(q.y))) { right2 = true; c2 = q.y; }
+    if (hstop<MAXHEAP>(sv, hval(c2))) break;
+    A[parent] = c2;
+    parent = child + (right2 ? 1 : 0);
+  }
+  A[parent] = s;
 }
 
 template <bool MAXHEAP>
-__device__ void heap_select(unsigned long long *A, int n, int extract) {
+__device__ void heap_build(unsigned long long *A, int n) {
   // build: roots n/2 .. 1; all roots of one tree level are independent (disjoint subtrees) and the
   // sequential order visits deeper levels first, so a level-synchronous sweep is equivalent.
   const int half = n >> 1;
@@ -233,32 +277,92 @@ __device__ void heap_select(unsigned long long *A, int n, int extract) {
       __syncthreads();
     }
   }
+}
+
+// Sequential extraction replay (beam.c:1370-1384): s = last; last = root; shrink; sift s from the root.
+template <bool MAXHEAP>
+__device__ void heap_extract_seq(unsigned long long *A, int n, int extract) {
   if (threadIdx.x == 0) {
     int m = n;
     while (m > n - extract) {
-      const unsigned long long s = A[m - 1];
-      A[m - 1] = A[0];
+      const unsigned long long s = A[m];
+      A[m] = A[1];
       m--;
-      if (m >= 1) {
-        // sift s down from the root of the shrunken heap (beam.c:1370-1384)
-        const float sv = hval(s);
-        int parent = 1, child;
-        while ((child = parent * 2) <= m) {
-          unsigned long long c = A[child - 1];
-          if (child < m) {
-            const unsigned long long c2 = A[child];
-            if (MAXHEAP ? (hval(c) < hval(c2)) : (hval(c) > hval(c2))) { child++; c = c2; }
-          }
-          if (MAXHEAP ? (sv >= hval(c)) : (sv <= hval(c))) break;
-          A[parent - 1] = c;
-          parent = child;
-        }
-        A[parent - 1] = s;
-      }
+      if (m >= 1) sift_root_2level<MAXHEAP>(A, s, m);
     }
   }
   __syncthreads();
 }
+
+// Pipelined extraction replay, warp 0, lock-step.  Lane k of the warp owns the extractions x with
+// x mod NL == k; every extraction in flight advances exactly one tree level per "tick" and a new one
+// starts at least two ticks after the previous one, so extraction x always works two levels above x-1:
+// it reads level L+1 one tick after x-1 wrote it and never touches a level x-1 is touching in the same
+// tick.  The only other coupling is at the bottom-right corner of the heap:
+//   * the extracted roots are NOT written into the tail slots while older extractions are in flight
+//     (those slots still belong to the older, larger heaps); they go to `outv`, the caller places them;
+//   * extraction x takes s = A[n-x] when it starts.  Sequential execution would hand it a different
+//     value only if an older extraction ends its sift exactly in that slot, and an extraction can only
+//     get there through the slot's ancestors.  So x does not start while an extraction in flight sits
+//     on an ancestor of slot n-x (a stall of a tick or two, ~0.6 tick per extraction on average);
+//     once no one does, A[n-x] is final.  No speculation, no rollback.
+// A single thread needs ~90 cycles per tree level (dependent-issue latency); the lock-step pipeline
+// retires one extraction every ~2.6 ticks instead of every ~11 levels.
+// (CPU model of exactly this schedule vs the sequential loop: tools/heapsim.cpp.)  Ends with a barrier.
+template <bool MAXHEAP>
+__device__ void heap_extract_pipelined(unsigned long long *A, const int n, const int extract, unsigned long long *outv) {
+  constexpr int NL = 16;
+  if (threadIdx.x < 32) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    bool act = false;
+    int par = 1, m = 0, lvl = 0;
+    unsigned long long s = 0ull; float sv = 0.0f;
+    int next_x = 0, wait = 0;
+    while (true) {
+      // (1) one level step for every extraction in flight
+      if (act) {
+        const int child = par * 2;
+        unsigned long long put = s;
+        bool stop = true;
+        if (child <= m) {
+          const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(A + child);
+          const bool right = (child < m) && hcmp<MAXHEAP>(hval(pr.x), hval(pr.y));
+          const unsigned long long c = right ? pr.y : pr.x;
+          if (!hstop<MAXHEAP>(sv, hval(c))) { stop = false; put = c; }
+          A[par] = put;
+          if (!stop) { par = child + (right ? 1 : 0); lvl++; }
+        } else A[par] = put;
+        act = !stop;
+      }
+      __syncwarp();
+      // (2) start the next extraction: >= 2 ticks after the previous start, its lane free, and nobody
+      //     in flight on an ancestor of its slot
+      if (--wait <= 0) {
+        if (next_x < extract) {
+          const int ms = n - next_x;
+          const int dms = 31 - __clz(ms);
+          const int ln = next_x & (NL - 1);
+          const bool blocks = act && ((lane == ln) || (dms >= lvl && (ms >> (dms - lvl)) == par));
+          if (!__any_sync(full, blocks)) {
+            if (lane == ln) {
+              s = A[ms]; sv = hval(s);
+              outv[next_x] = A[1];
+              m = ms - 1; par = 1; lvl = 0;
+              act = (m >= 1);
+            }
+            next_x++; wait = 2;
+          }
+        } else if (!__any_sync(full, act)) break;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// phase cycle accounting (thread 0 only; negligible cost)
+#define PROF_MARK(k) do { if (tid == 0) { long long _n = clock64(); s_prof[k] += _n - s_tprev; s_tprev = _n; } } while (0)
 
 // ---- the kernel ------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char beam_smem[];
@@ -270,14 +374,16 @@ beam_kernel(const BeamParams p) {
   const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
   const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
 
-  unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(beam_smem);   // [MAXT] sort keys, then heap entries
-  int *offs = reinterpret_cast<int *>(sbuf + MAXT);                               // [beam+2] candidate offsets per survivor
+  unsigned long long *heap = reinterpret_cast<unsigned long long *>(beam_smem);   // [MAXT+4] heap entries, slot h = heap index h
+  int *offs = reinterpret_cast<int *>(heap + MAXT + 4);                           // [beam+2] candidate payload offsets per survivor
+  int *poff = offs + (p.beam + 2);                                                // [beam+2] arrival-order bit positions per survivor
   __shared__ int s_warp[NWARP + 1];
-  __shared__ int s_ncre, s_E, s_natoms, s_ns, s_cur, s_overflow, s_found;
+  __shared__ int s_ncre, s_E, s_natoms, s_ns, s_cur, s_overflow, s_found, s_flag;
   __shared__ unsigned s_pmaxkey;
   __shared__ unsigned long long s_webest;
   __shared__ float s_thr;
   __shared__ long long s_outbase;
+  __shared__ long long s_prof[8], s_tprev;
 
   Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
   int *ord0 = p.order + (size_t)u * 2 * MAXT;
@@ -286,6 +392,9 @@ beam_kernel(const BeamParams p) {
   Cand *cand = p.cand + (size_t)u * MAXC;
   IsoCand *iso = p.iso + (size_t)u * max(p.n_iso, 1);
   WEnd *wend = p.wend + (size_t)u * MAXW;
+  unsigned *bits = p.bitmask + (size_t)u * (p.maxbits >> 5);
+  int *wpre = p.wordpre + (size_t)u * (p.maxbits >> 5);
+  unsigned long long *outv = p.outv + (size_t)u * (p.beam + 1);
   const long long a0 = p.atom_off[u];
   const int atom_cap = (int)(p.atom_off[u + 1] - a0);
   jb200_atom *araw = p.atoms_raw + a0;
@@ -295,7 +404,8 @@ beam_kernel(const BeamParams p) {
   jb200_utt_result *res = p.results + u;
   int *words = p.words + (size_t)u * MAX_WORDS;
 
-  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1; }
+  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1;
+                  for (int k = 0; k < 8; k++) s_prof[k] = 0; s_tprev = clock64(); }
   __syncthreads();
 
   // ================= frame 0: init_nodescore (beam.c:1631-1665) + first sort (:1883) =================
@@ -334,9 +444,10 @@ beam_kernel(const BeamParams p) {
     }
     if (tid == 0) { s_ncre = 0; s_webest = 0ull; s_pmaxkey = 0u; group0[t - 1] = s_natoms; }
     __syncthreads();
+    PROF_MARK(0);
 
     // ---- P1: per survivor: candidate counts, word ends, trellis atoms (save_trellis, beam.c:2209)
-    int cand_total;
+    int cand_total, nbits;
     {
       int carry_c = 0, carry_a = s_natoms, carry_w = 0;
       for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
@@ -358,6 +469,9 @@ beam_kernel(const BeamParams p) {
         const int ow = block_excl_scan(is_tr, s_warp, &tot_w);
         if (j < ns) {
           offs[j] = carry_c + oc;
+          // arrival-order position of this survivor's first candidate: its word-internal arcs,
+          // then (for a word end that may continue) one slot per isolated root
+          poff[j] = carry_c + oc + (carry_w + ow) * p.n_iso;
           if (is_we) {
             const int ai = carry_a + oa;
             if (ai < atom_cap) {
@@ -387,11 +501,15 @@ beam_kernel(const BeamParams p) {
         carry_c += tot_c; carry_a += tot_a; carry_w += tot_w;
       }
       cand_total = carry_c;
-      if (tid == 0) { offs[ns] = carry_c; s_natoms = min(carry_a, atom_cap); s_E = min(carry_w, MAXW); }
-      if (cand_total > MAXC) { if (tid == 0) s_overflow = 1; cand_total = 0; }
+      nbits = carry_c + carry_w * p.n_iso + p.n_shared;
+      if (tid == 0) { offs[ns] = carry_c; poff[ns] = carry_c + carry_w * p.n_iso; s_natoms = min(carry_a, atom_cap); s_E = min(carry_w, MAXW); }
+      if (cand_total > MAXC || carry_w > MAXW || nbits > p.maxbits) { if (tid == 0) s_overflow = 1; cand_total = 0; nbits = 0; }
     }
+    const int nwords = (nbits + 31) >> 5;
+    for (int w = tid; w < nwords; w += BEAM_THREADS) bits[w] = 0u;
     __syncthreads();
-    const int E = s_E;
+    PROF_MARK(1);
+    const int E = (nbits > 0) ? s_E : 0;
 
     // ---- P2a: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177)
     if (cand_total > 0) {
@@ -455,7 +573,7 @@ beam_kernel(const BeamParams p) {
     }
     // ---- P2c: best word end -> shared (1-gram factored) roots (beam_inter_word_factoring, :2549-2616)
     const unsigned long long webest = s_webest;
-    const bool have_we = (webest != 0ull);
+    const bool have_we = (webest != 0ull) && (nbits > 0);
     WEnd wbest; wbest.base = 0.0f; wbest.atom = -1; wbest.last_word = -1; wbest.transp2 = 0; wbest.j = 0; wbest.nintra = 0;
     if (have_we) {
       wbest = wend[(unsigned)(~(unsigned)(webest & 0xffffffffu))];
@@ -472,15 +590,18 @@ beam_kernel(const BeamParams p) {
       }
     }
     __syncthreads();
+    PROF_MARK(2);
 
-    // ---- P3: creators = candidates that were the first to reach their node
+    // ---- P3: creators = candidates that were the first to reach their node; one bit each at the
+    //          candidate's position in sequential arrival order
     for (int c = tid; c < cand_total; c += BEAM_THREADS) {
       const Cand cd = cand[c];
       if (!(cd.score > JB200_LOG_ZERO)) continue;
-      const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)(c - offs[cd.src]);
+      const int k = c - offs[cd.src];
+      const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)k;
       if ((unsigned)__ldcg(firstseq + cd.node) == seq) {
-        const int r = atomicAdd(&s_ncre, 1);
-        if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)cd.node;
+        const int pos = poff[cd.src] + k;
+        atomicOr(bits + (pos >> 5), 1u << (pos & 31));
       }
     }
     for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
@@ -488,48 +609,46 @@ beam_kernel(const BeamParams p) {
       if (ic.first_e < 0) continue;
       const WEnd wf = wend[ic.first_e];
       const unsigned seq = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
-      const int node = __ldg(p.iso_node + i);
-      if ((unsigned)__ldcg(firstseq + node) == seq) {
-        const int r = atomicAdd(&s_ncre, 1);
-        if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)node;
+      if ((unsigned)__ldcg(firstseq + __ldg(p.iso_node + i)) == seq) {
+        const int pos = poff[wf.j] + wf.nintra + i;
+        atomicOr(bits + (pos >> 5), 1u << (pos & 31));
       }
     }
     if (have_we) {
       for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
         const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
-        const int node = __ldg(p.shared_node + i);
-        if ((unsigned)__ldcg(firstseq + node) == seq) {
-          const int r = atomicAdd(&s_ncre, 1);
-          if (r < MAXT) sbuf[r] = ((unsigned long long)seq << 32) | (unsigned)node;
+        if ((unsigned)__ldcg(firstseq + __ldg(p.shared_node + i)) == seq) {
+          const int pos = poff[ns] + i;
+          atomicOr(bits + (pos >> 5), 1u << (pos & 31));
         }
       }
     }
     __syncthreads();
-    int ncre = s_ncre;
-    if (ncre > MAXT) { if (tid == 0) s_overflow = 1; ncre = MAXT; }
+    PROF_MARK(3);
 
-    // ---- P4: creation order = ascending seq (create_token numbering, beam.c:1147-1162)
-    int npow = 1; while (npow < ncre) npow <<= 1;
-    for (int i = ncre + tid; i < npow; i += BEAM_THREADS) sbuf[i] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (int i = tid; i < npow; i += BEAM_THREADS) {
-          const int ixj = i ^ jj;
-          if (ixj > i) {
-            const unsigned long long a = sbuf[i], b = sbuf[ixj];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { sbuf[i] = b; sbuf[ixj] = a; }
-          }
-        }
-        __syncthreads();
+    // ---- P4: creation order (create_token numbering, beam.c:1147-1162) = rank of the set bits
+    int ncre;
+    {
+      int carry = 0;
+      for (int w0 = 0; w0 < nwords; w0 += BEAM_THREADS) {
+        const int w = w0 + tid;
+        const int cnt = (w < nwords) ? __popc(__ldcg(bits + w)) : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt, s_warp, &tot);
+        if (w < nwords) wpre[w] = carry + ex;
+        carry += tot;
       }
+      ncre = carry;
     }
+    if (ncre > MAXT) { if (tid == 0) s_overflow = 1; ncre = 0; }
+    __syncthreads();
+    PROF_MARK(4);
 
-    // ---- P5: materialise tokens with the winner's content, add the output probability (beam.c:2944).
-    //          sbuf[r] is converted in place from sort key to heap entry (same thread reads then writes).
-    for (int r = tid; r < ncre; r += BEAM_THREADS) {
-      const int node = (int)(sbuf[r] & 0xffffffffu);
+    // ---- P5: materialise tokens with the winner's content, add the output probability (beam.c:2944)
+    auto materialise = [&](int pos, int node) {
+      const unsigned wbits = __ldcg(bits + (pos >> 5));
+      if (!((wbits >> (pos & 31)) & 1u)) return;
+      const int r = wpre[pos >> 5] + __popc(wbits & ((1u << (pos & 31)) - 1u));
       const unsigned long long bk = __ldcg(bestkey + node);
       const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
       const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
@@ -555,20 +674,68 @@ beam_kernel(const BeamParams p) {
       }
       nt.score += outprob_style(p, row, p.nodes[node].out, nt.tre_wid);
       tn[r] = nt;
-      sbuf[r] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
+      heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
       if (p.prune_width >= 0.0f) atomicMax(&s_pmaxkey, fkey(nt.score));
+    };
+    if (ncre > 0) {
+      for (int c = tid; c < cand_total; c += BEAM_THREADS) {
+        const Cand cd = cand[c];
+        if (!(cd.score > JB200_LOG_ZERO)) continue;
+        materialise(poff[cd.src] + (c - offs[cd.src]), cd.node);
+      }
+      for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
+        const IsoCand ic = iso[i];
+        if (ic.first_e < 0) continue;
+        const WEnd wf = wend[ic.first_e];
+        materialise(poff[wf.j] + wf.nintra + i, __ldg(p.iso_node + i));
+      }
+      if (have_we)
+        for (int i = tid; i < p.n_shared; i += BEAM_THREADS) materialise(poff[ns] + i, __ldg(p.shared_node + i));
     }
     __syncthreads();
+    PROF_MARK(5);
 
     // ---- P6: beam cut = the reference's heap select (sort_token_no_order, beam.c:1492-1520)
-    int ns_new, start;
+    int ns_new;
     {
       const int need = p.beam, rest = ncre - need;
-      if (need >= ncre) { start = 0; ns_new = ncre; }
-      else if (need < rest) { heap_select<true>(sbuf, ncre, need); start = ncre - need; ns_new = need; }
-      else { heap_select<false>(sbuf, ncre, rest); start = 0; ns_new = need; }
+      if (need >= ncre) {
+        ns_new = ncre;
+        for (int k = tid; k < ns_new; k += BEAM_THREADS) ordn[k] = k;
+      } else {
+        const bool upward = (need < rest);
+        const int extract = upward ? need : rest;
+        ns_new = need;
+        bool ok = false;
+        if (!p.force_seq_heap) {
+          if (upward) { heap_build<true>(heap, ncre); heap_extract_pipelined<true>(heap, ncre, extract, outv); }
+          else { heap_build<false>(heap, ncre); heap_extract_pipelined<false>(heap, ncre, extract, outv); }
+          ok = true;
+          if (ok) {
+            // survivors: upward = the extracted maxima, last extracted first (slots n-need+1..n);
+            //            downward = what is left of the heap (slots 1..need)
+            if (upward) for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
+            else for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
+          }
+        }
+        if (!ok || p.check_heap) {
+          // sequential replay from the token scores (JB200_FORCE_SEQ_HEAP, or self-check JB200_CHECK_HEAP)
+          __syncthreads();
+          for (int r = tid; r < ncre; r += BEAM_THREADS) heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(tn[r].score);
+          __syncthreads();
+          if (upward) { heap_build<true>(heap, ncre); heap_extract_seq<true>(heap, ncre, extract); }
+          else { heap_build<false>(heap, ncre); heap_extract_seq<false>(heap, ncre, extract); }
+          const int start = upward ? ncre - need : 0;
+          for (int k = tid; k < need; k += BEAM_THREADS) {
+            const int id = (int)(heap[start + k + 1] >> 32);
+            if (ok && ordn[k] != id) s_overflow = 4;      // self-check: pipelined replay disagrees
+            ordn[k] = id;
+          }
+          if (!ok && tid == 0) atomicAdd(p.misspec_counter, 1ull);
+        }
+      }
     }
-    for (int k = tid; k < ns_new; k += BEAM_THREADS) ordn[k] = (int)(sbuf[start + k] >> 32);
+    PROF_MARK(6);
     if (tid == 0) {
       counts[2 * t] = ncre; counts[2 * t + 1] = ns_new;
       s_ns = ns_new; s_cur = nxt;
@@ -680,6 +847,8 @@ beam_kernel(const BeamParams p) {
     r.status = status; r.n_frames = T; r.n_atoms = kept; r.n_words = nw; r.score = score;
     r.atom_offset = ob; r.word_offset = u * MAX_WORDS; r.overflow = s_overflow;
     *res = r;
+    PROF_MARK(7);
+    if (p.prof) for (int k = 0; k < 8; k++) p.prof[(size_t)u * 8 + k] = s_prof[k];
   }
 }
 
@@ -716,7 +885,7 @@ struct jb200_decoder {
   float *d_feats = nullptr, *d_rows = nullptr;
   int *d_frame_off = nullptr; long long *d_atom_off = nullptr;
   jb200_atom *d_atoms_out = nullptr; unsigned long long *d_atom_counter = nullptr;
-  jb200_utt_result *d_results = nullptr; int *d_words = nullptr;
+  jb200_utt_result *d_results = nullptr; int *d_words = nullptr; long long *d_prof = nullptr;
   // host results (pinned)
   jb200_utt_result *h_results = nullptr; jb200_atom *h_atoms = nullptr; int *h_words = nullptr;
   unsigned long long *h_counter = nullptr;
@@ -851,8 +1020,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     }
   }
   // work areas
-  int maxt = 1; while (maxt < 2 * t->beam_width + t->n_start + 64) maxt <<= 1;
-  if (const char *e = getenv("JB200_MAXT")) { int v = atoi(e); maxt = 1; while (maxt < v) maxt <<= 1; }
+  int maxt = (4 * t->beam_width + t->n_start + 64 + 3) & ~3;   // the reference starts at 2*beam+startnum and grows on demand; we size for 4*beam and flag overflow
+  if (const char *e = getenv("JB200_MAXT")) maxt = (std::max(atoi(e), 64) + 3) & ~3;
   P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.tok));
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.order));
@@ -861,6 +1030,14 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.cand));
   TRY(dev_alloc(d, (size_t)max_utts * std::max(t->n_iso, 1), &P.iso));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxw, &P.wend));
+  P.maxbits = (P.maxc + std::min(P.maxw, 256) * std::max(t->n_iso, 1) + t->n_shared + 63) & ~31;
+  TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.bitmask));
+  TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.wordpre));
+  TRY(dev_alloc(d, (size_t)max_utts * (t->beam_width + 1), &P.outv));
+  TRY(dev_alloc(d, 1, &P.misspec_counter));
+  TRYC(cudaMemset(P.misspec_counter, 0, sizeof(unsigned long long)));
+  P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
+  P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
   {
     size_t tot = (size_t)max_utts * n;
     fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.firstseq, P.bestkey, tot);
@@ -876,6 +1053,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRY(dev_alloc(d, 1, &d->d_atom_counter));
   TRY(dev_alloc(d, (size_t)max_utts, &d->d_results));
   TRY(dev_alloc(d, (size_t)max_utts * MAX_WORDS, &d->d_words));
+  TRY(dev_alloc(d, (size_t)max_utts * 8, &d->d_prof));
   TRY(dev_alloc(d, (size_t)max_utts + 1, &d->d_frame_off));
   TRY(dev_alloc(d, (size_t)max_utts + 1, &d->d_atom_off));
   TRY(dev_alloc(d, (size_t)max_frames * d->dim, &d->d_feats));
@@ -884,7 +1062,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_atoms, sizeof(jb200_atom) * (size_t)d->atoms_cap));
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
-  d->smem_bytes = (size_t)maxt * 8 + (size_t)(t->beam_width + 2) * 4;
+  d->smem_bytes = (size_t)(maxt + 4) * 8 + (size_t)(t->beam_width + 2) * 4 * 2;
   TRYC(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
   {
     int per_sm = 0, sms = 0;
@@ -926,7 +1104,7 @@ static int launch_beam(jb200_decoder *d, int n_utts) {
   BeamParams P = d->P;
   P.rows = d->d_rows; P.row_stride = d->row_stride; P.frame_off = d->d_frame_off;
   P.atom_off = d->d_atom_off; P.atoms_out = d->d_atoms_out; P.atom_counter = d->d_atom_counter;
-  P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words;
+  P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words; P.prof = d->d_prof;
   beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   JB_LAUNCH_CHECK();
   return JB200_OK;
@@ -966,6 +1144,21 @@ extern "C" int jb200_decoder_sync_timing(jb200_decoder *d) {
   cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
   d->last_ms[3] = 0.0f;
   return JB200_OK;
+}
+
+extern "C" int jb200_decoder_phase_cycles(jb200_decoder *d, int64_t *cycles, int n_utts) {
+  if (!d || !cycles || n_utts < 1 || n_utts > d->last_n) { set_error("bad argument"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaMemcpy(cycles, d->d_prof, sizeof(long long) * 8 * (size_t)n_utts, cudaMemcpyDeviceToHost));
+  return JB200_OK;
+}
+
+extern "C" int64_t jb200_decoder_misspeculations(jb200_decoder *d) {
+  if (!d) return -1;
+  unsigned long long v = 0;
+  cudaSetDevice(d->device);
+  if (cudaMemcpy(&v, d->P.misspec_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
 }
 
 extern "C" int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d) { return d ? d->last_d2h : 0; }

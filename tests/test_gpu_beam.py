@@ -87,3 +87,25 @@ def test_capacity_errors_are_loud():
         dec.decode([g.feats[0], g.feats[0]])
     with pytest.raises(capi.Jb200Error):
         dec.decode([g.feats[0]])          # 150 frames > 64
+
+
+def test_pipelined_heap_replay_agrees_with_sequential_replay(monkeypatch):
+    """JB200_CHECK_HEAP=1 makes the kernel run BOTH heap replays every frame and flag any difference
+    in the survivor order (overflow code 4)."""
+    monkeypatch.setenv("JB200_CHECK_HEAP", "1")
+    for case in ("small_b100", "small_safe"):
+        g = Golden(case)
+        am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+        dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
+        res = dec.decode(g.feats)
+        for r, u in zip(res, g.utts):
+            _check(r, u)
+
+
+def test_forced_sequential_heap_gives_same_trellis(monkeypatch):
+    monkeypatch.setenv("JB200_FORCE_SEQ_HEAP", "1")
+    g = Golden("small_b100")
+    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
+    for r, u in zip(dec.decode(g.feats), g.utts):
+        _check(r, u)

@@ -83,3 +83,23 @@ def test_fast_mode_scores_within_tolerance_and_decodes(full):
     a, b = am.score(x), full["am"].score(x)
     rel = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)
     assert rel.max() <= 1e-4      # BASELINE.json north_star tolerance on float log-likelihoods
+
+
+def test_full_size_heap_self_check(monkeypatch, oracle_lib):
+    """beam 800 over ~2400 tokens per frame: pipelined vs sequential heap replay on every frame."""
+    if not workload.ready(NAME):
+        pytest.skip("workloads/tri20k not prepared")
+    monkeypatch.setenv("JB200_CHECK_HEAP", "1")
+    blob = refdump.load_blob(workload.path(NAME, "model.jb2m"))
+    ds = desc.Descriptors(blob)
+    am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(ds, am, max_utts=8, max_frames=8 * 600)
+    m = workload.synth_model(NAME)
+    feats = workload.sample_batch(m, 6, 600, seed=77) + [m.sample_noise(np.random.default_rng(8), 300)]
+    res = dec.decode(feats)
+    assert all(r["overflow"] == 0 and r["status"] == 0 for r in res[:6])
+    assert res[6]["overflow"] == 0
+    x = feats[0]
+    o = oracle_lib.beam_decode(ds, oracle_lib.gmm_score(ds, x))
+    ok, why = atoms_equal(res[0]["atoms"], o["atoms"])
+    assert ok, why
