@@ -182,40 +182,11 @@ def reference_main(a):
 
 
 # --------------------------------------------------------------------------------------- product arm
-def broadcast_blob(blob, rank, world, device):
-    """Init-time NCCL broadcast of the flattened model from rank 0."""
-    import torch
-    import torch.distributed as dist
-    if world == 1:
-        return blob
-    manifest = [None]
-    if rank == 0:
-        manifest[0] = [(k, str(v.dtype), int(v.size)) for k, v in blob.items()]
-    dist.broadcast_object_list(manifest, src=0)
-    total = sum(np.dtype(dt).itemsize * n + (-(np.dtype(dt).itemsize * n) % 16) for _, dt, n in manifest[0])
-    flat = torch.empty(total, dtype=torch.uint8, device=device)
-    if rank == 0:
-        host = np.zeros(total, np.uint8)
-        pos = 0
-        for k, dt, n in manifest[0]:
-            raw = blob[k].tobytes()
-            host[pos:pos + len(raw)] = np.frombuffer(raw, np.uint8)
-            pos += len(raw) + (-len(raw) % 16)
-        flat.copy_(torch.from_numpy(host))
-    dist.broadcast(flat, src=0)
-    host = flat.cpu().numpy()
-    out, pos = {}, 0
-    for k, dt, n in manifest[0]:
-        nb = np.dtype(dt).itemsize * n
-        out[k] = host[pos:pos + nb].view(dt).copy()
-        pos += nb + (-nb % 16)
-    return out
-
-
 def product_main(a):
     import torch
     import torch.distributed as dist
     from julius_b200 import capi, desc, refdump, workload
+    from julius_b200.dist import broadcast_blob
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
