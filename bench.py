@@ -329,7 +329,7 @@ def product_main(a):
                          "kernel_ms": {"gmm_score_kernel": gmm_ms, "beam_kernel": bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
                          "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
-                         "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_select", "rest"), phase)},
+                         "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_extract", "heap_build"), phase)},
                          "beam_tokens_per_frame": tokens_per_frame, "beam_created_per_frame": created_per_frame},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                     "ms_per_step": e2e_ms_max / a.steps},

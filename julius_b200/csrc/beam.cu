@@ -367,7 +367,10 @@ __device__ void heap_extract_pipelined(unsigned long long *A, const int n, const
 // ---- the kernel ------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char beam_smem[];
 
-__global__ void __launch_bounds__(BEAM_THREADS)
+#ifndef JB200_BEAM_MINBLOCKS
+#define JB200_BEAM_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(BEAM_THREADS, JB200_BEAM_MINBLOCKS)
 beam_kernel(const BeamParams p) {
   const int u = blockIdx.x;
   const int tid = threadIdx.x;
