@@ -288,3 +288,58 @@ def read_htk_param(path: str):
         D = size // 4
         data = np.frombuffer(f.read(T * D * 4), dtype=">f4").astype(np.float32).reshape(T, D)
     return data, kind
+
+
+# ---------------------------------------------------------------------------------------- DNN-HMM
+@dataclasses.dataclass
+class DnnConfig:
+    in_dim: int = 120          # feature_len * context_len (already spliced)
+    feature_len: int = 40
+    context_len: int = 3
+    hidden: int = 64
+    layers: int = 2
+    seed: int = 5
+
+
+def write_dnn(outdir: str, n_states: int, cfg: DnnConfig) -> dict:
+    """Random-init DNN in the reference's file formats (libsent/src/phmm/calc_dnn.c:225-336,
+    libjulius/src/m_jconf.c:579-733): W as C-order (out,in) '<f4' .npy, biases (out,1), prior file
+    'state_id prior', and the dnnconf tying them together.  Returns the arrays."""
+    rng = np.random.default_rng(cfg.seed)
+    os.makedirs(outdir, exist_ok=True)
+    dims = [cfg.in_dim] + [cfg.hidden] * cfg.layers
+    arrays = {}
+    lines = ["feature_type USER", "feature_options -notypecheck", f"feature_len {cfg.feature_len}",
+             f"context_len {cfg.context_len}", f"input_nodes {cfg.in_dim}", f"output_nodes {n_states}",
+             f"hidden_nodes {cfg.hidden}", f"hidden_layers {cfg.layers}"]
+    for i in range(cfg.layers):
+        w = (rng.standard_normal((dims[i + 1], dims[i])) * (1.5 / np.sqrt(dims[i]))).astype("<f4")
+        b = (rng.standard_normal((dims[i + 1], 1)) * 0.1).astype("<f4")
+        np.save(os.path.join(outdir, f"W{i + 1}.npy"), w)
+        np.save(os.path.join(outdir, f"B{i + 1}.npy"), b)
+        arrays[f"W{i + 1}"], arrays[f"B{i + 1}"] = w, b
+        lines += [f"W{i + 1} W{i + 1}.npy", f"B{i + 1} B{i + 1}.npy"]
+    wo = (rng.standard_normal((n_states, cfg.hidden)) * (3.0 / np.sqrt(cfg.hidden))).astype("<f4")
+    bo = (rng.standard_normal((n_states, 1)) * 0.1).astype("<f4")
+    np.save(os.path.join(outdir, "Wo.npy"), wo)
+    np.save(os.path.join(outdir, "Bo.npy"), bo)
+    prior = rng.dirichlet(np.full(n_states, 5.0))
+    with open(os.path.join(outdir, "prior.txt"), "w") as f:
+        for i, p in enumerate(prior):
+            f.write(f"{i} {p:.8e}\n")
+    lines += ["output_W Wo.npy", "output_B Bo.npy", "state_prior prior.txt", "state_prior_factor 1.0",
+              "state_prior_log10nize yes", "batch_size 1", "num_threads 1"]
+    with open(os.path.join(outdir, "dnnconf"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    arrays.update(Wo=wo, Bo=bo, prior=prior)
+    return arrays
+
+
+def sample_dnn_input(rng: np.random.Generator, n_frames: int, in_dim: int) -> np.ndarray:
+    """Smooth random trajectories (AR(1)) so that consecutive frames favour similar states."""
+    x = np.empty((n_frames, in_dim), np.float32)
+    v = rng.standard_normal(in_dim)
+    for t in range(n_frames):
+        v = 0.9 * v + 0.45 * rng.standard_normal(in_dim)
+        x[t] = v
+    return x

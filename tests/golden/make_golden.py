@@ -30,6 +30,10 @@ CASES = {
     "small_b100": ("small", 2, 200, 1, ["-b", "100"]),
     "small_safe": ("small", 1, 150, 0, ["-gprune", "safe", "-tmix", "2", "-b", "60", "-iwcd1", "max"]),
 }
+# DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
+DNN_CASES = {
+    "small_dnn": ("small", dict(in_dim=120, feature_len=40, context_len=3, hidden=128, layers=3), 2, 150, ["-b", "150"]),
+}
 
 
 def main():
@@ -45,6 +49,29 @@ def main():
         np.savez_compressed(os.path.join(dst, "feats.npz"), **feats)
         with open(os.path.join(dst, "meta.json"), "w") as f:
             json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "summary": out.strip().splitlines()[-1]}, f, indent=1)
+        shutil.rmtree(tmp)
+        print(name, "->", dst)
+    for name, (preset, dkw, nu, nf, extra) in DNN_CASES.items():
+        tmp = tempfile.mkdtemp(prefix="jb200_golden_")
+        cfg = synth.SynthConfig.preset(preset)
+        m = synth.SynthModel(cfg)
+        m.write_all(tmp)
+        dc = synth.DnnConfig(**dkw)
+        synth.write_dnn(tmp, cfg.n_states, dc)
+        rng = np.random.default_rng(17)
+        files = []
+        for u in range(nu):
+            fn = os.path.join(tmp, f"u{u}.mfc")
+            synth.write_htk_param(fn, synth.sample_dnn_input(rng, nf, dc.in_dim), parmkind=synth.PARMKIND_USER)
+            files.append(fn)
+        dump, out = ffi.run_ref(tmp, files, extra_args=["-dnnconf", "dnnconf"] + extra, export=os.path.join(tmp, "model.jb2m"))
+        dst = os.path.join(HERE, name)
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(tmp, "model.jb2m"), dst)
+        shutil.copy(dump, os.path.join(dst, "out.jrf"))
+        np.savez_compressed(os.path.join(dst, "feats.npz"), **{f"u{i}": synth.read_htk_param(fn)[0] for i, fn in enumerate(files)})
+        with open(os.path.join(dst, "meta.json"), "w") as f:
+            json.dump({"preset": preset, "dnn": dkw, "extra_args": extra, "n_utts": len(files), "summary": out.strip().splitlines()[-1]}, f, indent=1)
         shutil.rmtree(tmp)
         print(name, "->", dst)
 

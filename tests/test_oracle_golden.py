@@ -44,3 +44,16 @@ def test_cdset_scores_consistent_with_states(oracle_lib):
     for c in range(0, cd.shape[1], 37):
         v = np.sort(st[5, ids[off[c]:off[c + 1]]])[::-1][:3]
         assert abs(cd[5, c] - v.astype(np.float64).mean()) < 1e-3
+
+
+def test_dnn_restatement_bit_exact_and_beam_on_dnn_scores(oracle_lib):
+    """DNN-HMM: the restatement of dnn_calc_outprob (x86 FMA GEMV order, logistic table, addlog
+    softmax, prior) equals the compiled reference bit for bit; the beam restatement runs on it."""
+    g = Golden("small_dnn")
+    for u, x in zip(g.utts, g.feats):
+        sc = oracle_lib.dnn_score(g.ds, x)
+        assert np.array_equal(sc.view(np.uint32), u.outprob.view(np.uint32))
+        r = oracle_lib.beam_decode(g.ds, u.outprob)
+        ok, why = atoms_equal(r["atoms"], u.atoms)
+        assert ok, why
+        assert r["words"] == u.words and r["status"] == u.status
