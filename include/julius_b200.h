@@ -72,6 +72,21 @@ int jb200_gmm_cdsets_device(jb200_gmm *h, float *d_rows, int T, void *stream);
 int jb200_gmm_gauss_host(jb200_gmm *h, const float *feat, float *gauss);
 
 /* ------------------------------------------------------------------------------------
+ * DNN-HMM state scorer (tensor cores).  Stands in for, for all frames of a batch at once,
+ *   dnn_calc_outprob()   libsent/src/phmm/calc_dnn.c:774-868   (GEMV stack, table logistic,
+ *                        log-softmax through addlog_array, minus log10 state prior)
+ *   cuda_calc_outprob()  libsent/src/phmm/calc_dnn_cuda.cu:294-321 (the reference's own GPU path)
+ * in [T][in_dim] already spliced feature vectors -> scores [T][out_dim], log10.
+ * Arithmetic: bf16 x3 split products with fp32 accumulation (<= 1e-4 relative).
+ * ---------------------------------------------------------------------------------- */
+typedef struct jb200_dnn jb200_dnn;
+int jb200_dnn_create(const jb200_dnn_desc *desc, int device, jb200_dnn **out);
+void jb200_dnn_destroy(jb200_dnn *h);
+int jb200_dnn_in_dim(const jb200_dnn *h);
+int jb200_dnn_out_dim(const jb200_dnn *h);
+int jb200_dnn_score_host(jb200_dnn *h, const float *in, int T, float *scores);
+
+/* ------------------------------------------------------------------------------------
  * Pass-1 decoder (lexicon-tree token passing).  Stands in for
  *   get_back_trellis_init/_proceed/_end, finalize_1st_pass   libjulius/src/beam.c:1825,2663,3052,3133
  *   outprob_style()                                         libjulius/src/outprob_style.c:354-494
@@ -107,6 +122,9 @@ typedef struct {
 int jb200_decoder_create(const jb200_tree_desc *tree, jb200_gmm *am, int max_utts, int max_frames,
                          jb200_decoder **out);
 void jb200_decoder_destroy(jb200_decoder *d);
+/* DNN-HMM: score frames with `dnn` instead of the GMMs of `am` (am then only carries the state /
+ * cd-set layout: a descriptor with n_gauss == 0 is accepted by jb200_gmm_create for this purpose). */
+int jb200_decoder_attach_dnn(jb200_decoder *d, jb200_dnn *dnn);
 
 /* End-to-end: host feature vectors -> GPU scoring -> GPU beam -> host results.
  *   feats       [sum T_u][dim]   concatenated utterances (host)

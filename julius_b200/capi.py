@@ -46,6 +46,13 @@ def lib():
         L.jb200_gmm_score_device.argtypes = [vp, vp, C.c_int, vp, vp]
         L.jb200_gmm_cdsets_device.argtypes = [vp, vp, C.c_int, vp]
         L.jb200_gmm_gauss_host.argtypes = [vp, D.F, D.F]
+        if hasattr(L, "jb200_dnn_create"):
+            L.jb200_dnn_create.argtypes = [C.POINTER(D.DnnDesc), C.c_int, C.POINTER(vp)]
+            L.jb200_dnn_destroy.argtypes = [vp]
+            L.jb200_dnn_in_dim.argtypes = [vp]
+            L.jb200_dnn_out_dim.argtypes = [vp]
+            L.jb200_dnn_score_host.argtypes = [vp, D.F, C.c_int, D.F]
+            L.jb200_decoder_attach_dnn.argtypes = [vp, vp]
         if hasattr(L, "jb200_decoder_create"):
             L.jb200_decoder_create.argtypes = [C.POINTER(D.TreeDesc), vp, C.c_int, C.c_int, C.POINTER(vp)]
             L.jb200_decoder_destroy.argtypes = [vp]
@@ -132,6 +139,39 @@ class GmmScorer:
             pass
 
 
+class DnnScorer:
+    """DNN-HMM forward on the tensor cores (dnn_calc_outprob)."""
+
+    def __init__(self, ds: D.Descriptors, device: int = 0):
+        self.ds = ds
+        self._h = C.c_void_p()
+        _check(lib().jb200_dnn_create(C.byref(ds.dnn), device, C.byref(self._h)), "jb200_dnn_create")
+        self.in_dim = lib().jb200_dnn_in_dim(self._h)
+        self.out_dim = lib().jb200_dnn_out_dim(self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def score(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        T = x.shape[0]
+        out = np.empty((T, self.out_dim), np.float32)
+        _check(lib().jb200_dnn_score_host(self._h, _f(x), T, _f(out)), "jb200_dnn_score_host")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().jb200_dnn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Decoder:
     """Batched pass-1 decoder (get_back_trellis_* / outprob_style / factoring lookups on the GPU)."""
 
@@ -140,6 +180,11 @@ class Decoder:
         self._h = C.c_void_p()
         _check(lib().jb200_decoder_create(C.byref(ds.tree), am.handle, max_utts, max_frames, C.byref(self._h)),
                "jb200_decoder_create")
+        self.dnn = None
+
+    def attach_dnn(self, dnn: "DnnScorer"):
+        _check(lib().jb200_decoder_attach_dnn(self._h, dnn.handle), "jb200_decoder_attach_dnn")
+        self.dnn = dnn
 
     @staticmethod
     def _offsets(lengths):

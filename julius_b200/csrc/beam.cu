@@ -33,7 +33,9 @@
 #include <algorithm>
 
 struct jb200_gmm;
+struct jb200_dnn;
 namespace jb200 {
+int dnn_forward_device(jb200_dnn *h, const float *d_in, int T, float *d_rows, int row_stride, cudaStream_t st);
 int gmm_device(const jb200_gmm *h);
 int gmm_dim(const jb200_gmm *h);
 int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st);
@@ -877,6 +879,7 @@ using namespace jb200;
 
 struct jb200_decoder {
   jb200_gmm *am = nullptr;
+  jb200_dnn *dnn = nullptr;
   int device = 0, dim = 0, S = 0, row_stride = 0;
   int max_utts = 0, max_frames = 0;         // per batch: utterances, total frames
   int atoms_per_frame = 64;
@@ -1156,6 +1159,24 @@ extern "C" int jb200_decoder_phase_cycles(jb200_decoder *d, int64_t *cycles, int
   return JB200_OK;
 }
 
+extern "C" int jb200_dnn_in_dim(const jb200_dnn *h);
+extern "C" int jb200_dnn_out_dim(const jb200_dnn *h);
+extern "C" int jb200_decoder_attach_dnn(jb200_decoder *d, jb200_dnn *dnn) {
+  if (!d || !dnn) { set_error("null argument"); return JB200_ERR_ARG; }
+  if (jb200_dnn_out_dim(dnn) != d->S) { set_error("DNN has %d outputs but the HMM set has %d states", jb200_dnn_out_dim(dnn), d->S); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  const int dim = jb200_dnn_in_dim(dnn);
+  if (dim != d->dim) {
+    // the feature buffer was sized for the AM's dimension; re-size it for the DNN's input width
+    float *nf = nullptr;
+    JB_CUDA(cudaMalloc(&nf, sizeof(float) * (size_t)d->max_frames * dim));
+    d->dev_allocs.push_back(nf);
+    d->d_feats = nf; d->dim = dim;
+  }
+  d->dnn = dnn;
+  return JB200_OK;
+}
+
 extern "C" int64_t jb200_decoder_misspeculations(jb200_decoder *d) {
   if (!d) return -1;
   unsigned long long v = 0;
@@ -1171,7 +1192,9 @@ extern "C" int jb200_decode_batch_device(jb200_decoder *d, const float *d_feats,
   int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
   JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
-  rc = gmm_launch_states(d->am, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream); if (rc) return rc;
+  rc = d->dnn ? dnn_forward_device(d->dnn, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream)
+              : gmm_launch_states(d->am, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream);
+  if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
   rc = launch_beam(d, n_utts); if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[3], d->stream));
@@ -1184,7 +1207,9 @@ extern "C" int jb200_decode_batch_host(jb200_decoder *d, const float *feats, con
   JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
   JB_CUDA(cudaMemcpyAsync(d->d_feats, feats, sizeof(float) * (size_t)d->last_total_frames * d->dim, cudaMemcpyHostToDevice, d->stream));
   JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
-  rc = gmm_launch_states(d->am, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream); if (rc) return rc;
+  rc = d->dnn ? dnn_forward_device(d->dnn, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream)
+              : gmm_launch_states(d->am, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream);
+  if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
   rc = launch_beam(d, n_utts); if (rc) return rc;
   return jb200_decoder_fetch(d);

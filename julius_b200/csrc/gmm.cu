@@ -353,11 +353,11 @@ extern "C" int jb200_gmm_create(const jb200_gmm_desc *d, int device, int mode, j
   std::vector<GmmTile> tiles;
   std::vector<int> mixcnt(h->S);
   for (int s = 0; s < h->S; s++) {
-    mixcnt[s] = d->state_off[s + 1] - d->state_off[s];
+    mixcnt[s] = (h->G > 0) ? d->state_off[s + 1] - d->state_off[s] : 0;
     if (mixcnt[s] > GMM_TILE_GAUSS) { set_error("state %d has %d mixtures (max %d)", s, mixcnt[s], GMM_TILE_GAUSS); delete h; return JB200_ERR_UNSUPPORTED; }
   }
   for (int s = 0; s < h->S;) {
-    GmmTile t{s, 0, d->state_off[s], 0};
+    GmmTile t{s, 0, (h->G > 0) ? d->state_off[s] : 0, 0};
     while (s < h->S && t.ns < GMM_TILE_STATES && t.ng + mixcnt[s] <= GMM_TILE_GAUSS) { t.ng += mixcnt[s]; t.ns++; s++; }
     if (t.ng > 0) tiles.push_back(t);
     else if (t.ns == 0) s++;   // cannot happen (mixcnt<=TILE_GAUSS)
@@ -369,7 +369,7 @@ extern "C" int jb200_gmm_create(const jb200_gmm_desc *d, int device, int mode, j
   memcpy(tb.data() + tiles.size() * sizeof(GmmTile), mixcnt.data(), mixcnt.size() * sizeof(int));
 
   JB_CUDA(cudaMalloc(&h->d_pk, pk.size() * sizeof(float) + 16));
-  JB_CUDA(cudaMemcpy(h->d_pk, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!pk.empty()) JB_CUDA(cudaMemcpy(h->d_pk, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
   JB_CUDA(cudaMalloc(&h->d_tiles, tile_bytes + 16));
   JB_CUDA(cudaMemcpy(h->d_tiles, tb.data(), tile_bytes, cudaMemcpyHostToDevice));
   if (h->C > 0) {
@@ -442,6 +442,7 @@ namespace jb200 {
 // state columns only, caller-chosen row stride (used by the decoder, which evaluates cd sets on demand)
 int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st) {
   if (T <= 0) return JB200_OK;
+  if (h->G == 0) { set_error("this scorer carries no Gaussians (DNN-HMM layout only)"); return JB200_ERR_ARG; }
   JB_CUDA(cudaSetDevice(h->device));
   switch (h->D) {
     case 39: return launch_gmm<39>(h, d_feats, T, d_rows, row_stride, st);
