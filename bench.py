@@ -127,7 +127,8 @@ def run_reference_sample(workload_name: str, n_procs: int, utts_per_proc: int, n
         files = []
         for ui in range(utts_per_proc):
             fn = os.path.join(tmp, f"p{pi}_u{ui}.mfc")
-            synth.write_htk_param(fn, m.sample_utterance(rng, n_frames)[0])
+            x = workload.sample_inputs(workload_name, m, 1, n_frames, seed=int(rng.integers(1 << 30)))[0]
+            workload.write_input(workload_name, fn, x)
             files.append(fn)
         args = [jref, "-dump", os.path.join(tmp, f"p{pi}.jrf")] + workload.ref_args(workload_name)
         p = subprocess.Popen(args, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
@@ -204,9 +205,15 @@ def product_main(a):
     blob = refdump.load_blob(workload.path(a.workload, "model.jb2m")) if rank == 0 else None
     blob = broadcast_blob(blob, rank, world, device)
     ds = desc.Descriptors(blob)
-    S, M_total, D = ds.gmm.n_states, ds.gmm.n_gauss, ds.gmm.dim
-
-    am = capi.GmmScorer(ds, device=local, mode=capi.GMM_EXACT if a.mode == "exact" else capi.GMM_FAST)
+    use_dnn = ds.dnn is not None
+    if use_dnn:
+        S, M_total, D = ds.n_states, 0, ds.dnn.in_dim
+        am = capi.GmmScorer(ds, device=local, gmm_desc=ds.cd_only_gmm())
+        dnn = capi.DnnScorer(ds, device=local)
+        dnn_flops_per_frame = 2.0 * sum(int(ds.dnn.layer_in[i]) * int(ds.dnn.layer_out[i]) for i in range(ds.dnn.n_layers))
+    else:
+        S, M_total, D = ds.gmm.n_states, ds.gmm.n_gauss, ds.gmm.dim
+        am = capi.GmmScorer(ds, device=local, mode=capi.GMM_EXACT if a.mode == "exact" else capi.GMM_FAST)
     T = a.frames
     if a.utts:
         B = a.utts
@@ -215,6 +222,8 @@ def product_main(a):
         B = max(1, probe.resident_utts())      # one resident wave of thread blocks
         probe.close()
     dec = capi.Decoder(ds, am, max_utts=B, max_frames=B * T)
+    if use_dnn:
+        dec.attach_dnn(dnn)
 
     # synthetic MFCC batches sampled from the model along <s> w.. </s> paths, different per rank and step
     m = workload.synth_model(a.workload)
@@ -223,7 +232,7 @@ def product_main(a):
     host_batches, dev_batches = [], []
     for bi in range(n_batches):
         # a pool of 32 sampled utterances tiled to B (sampling 592k frames in numpy is the slow part)
-        pool = workload.sample_batch(m, min(B, 32), T, seed=100 + 17 * rank + bi)
+        pool = workload.sample_inputs(a.workload, m, min(B, 32), T, seed=100 + 17 * rank + bi)
         feats = np.concatenate([pool[i % len(pool)] for i in range(B)], 0)
         hb = torch.from_numpy(feats).pin_memory()
         host_batches.append(hb)
@@ -309,28 +318,42 @@ def product_main(a):
         created_per_frame = float(counts[:, 0].mean())
         gmm_bytes = M_total * ALG_GMM_BYTES_PER_GAUSS + B * T * (D * 4 + 4 * S)
         beam_bytes = B * T * tokens_per_frame * ALG_BEAM_BYTES_PER_TOKEN
+        score_name = "dnn_gemm_kernel (x%d layers)" % ds.dnn.n_layers if use_dnn else "gmm_score_kernel"
         if bm_ms >= gmm_ms:
             dom, dom_ms, dom_bytes = "beam_kernel", bm_ms, beam_bytes
         else:
-            dom, dom_ms, dom_bytes = "gmm_score_kernel", gmm_ms, gmm_bytes
+            dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
         ach = dom_bytes / (dom_ms / 1000.0) / 1e9
+        tensor = None
+        if use_dnn:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
+            tach = B * T * dnn_flops_per_frame / (gmm_ms / 1000.0) / 1e12
+            tensor = {"bound": "tensor", "kernel": score_name, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                      "note": "algorithmic flops (2*in*out per layer per frame); the kernel issues 3 bf16 MMAs per product term "
+                              "(hi.hi+hi.lo+lo.hi) to meet the 1e-4 tolerance, so 1/3 of peak is the ceiling of this formulation",
+                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"}
         line = {
             "metric": "frames/sec (xRT) 20k-word triphone decode", "value": value, "unit": "frames/s", "xRT": value / 100.0,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall_ms_max / a.steps, "device_event_ms_per_step": dev_ms_max / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{a.workload}: tied-state triphone GMM {S} states x 16 mix x {D} dim, 20k-word 2-gram "
-                                   f"(BASELINE configs[1]), beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
-                                   f"GMM arithmetic mode {a.mode}",
+            "config": {"workload": (f"{a.workload}: DNN-HMM {D} -> {ds.dnn.n_layers - 1} x {int(ds.dnn.layer_out[0])} logistic -> {S} states "
+                                    f"(BASELINE configs[3] shape), 20k-word 2-gram, beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
+                                    f"bf16x3 tensor-core arithmetic") if use_dnn else
+                                   (f"{a.workload}: tied-state triphone GMM {S} states x 16 mix x {D} dim, 20k-word 2-gram "
+                                    f"(BASELINE configs[1]), beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
+                                    f"GMM arithmetic mode {a.mode}"),
                        "utts_per_gpu": B, "frames_per_utt": T,
                        "l2": "per-step working set (score matrix %.1f GB) exceeds L2; input batch alternates" % (B * T * S * 4 / 1e9),
                        "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": {"gmm_score_kernel": gmm_ms, "beam_kernel": bm_ms},
+                         "kernel_ms": {score_name: gmm_ms, "beam_kernel": bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
                          "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
                          "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_extract", "heap_build"), phase)},
                          "beam_tokens_per_frame": tokens_per_frame, "beam_created_per_frame": created_per_frame},
+            "roofline_scoring": tensor,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                     "ms_per_step": e2e_ms_max / a.steps},
             "gpu_launches": int(launches),

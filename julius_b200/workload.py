@@ -29,7 +29,10 @@ WORKLOADS = {
     "mono100": ("mono100", []),                       # BASELINE configs[0]
     "tri20k": ("tri20k", []),                         # configs[1]: 3k states x 16 mix, 20k words, beam 800 (auto)
     "tri20k_gbeam": ("tri20k", ["-gprune", "beam"]),  # configs[2]: same with -gprune beam
+    "dnn20k": ("tri20k", ["-dnnconf", "@DNN@"]),      # configs[3]: DNN-HMM 528 -> 7x2048 -> 3000, 20k words
 }
+# DNN shapes (BASELINE configs[3]: ENVR-v5.4 shape 7x2048 sigmoid, 48x11 input)
+DNN_SHAPES = {"dnn20k": dict(in_dim=528, feature_len=48, context_len=11, hidden=2048, layers=7, seed=9)}
 
 
 def path(name: str, *parts) -> str:
@@ -63,11 +66,19 @@ def ensure(name: str, verbose: bool = False) -> bool:
     if not os.path.exists(os.path.join(mdir, "lm.arpa")):
         m.write_all(mdir)
     os.makedirs(path(name), exist_ok=True)
+    is_dnn = name in DNN_SHAPES
+    if is_dnn:
+        dc = synth.DnnConfig(**DNN_SHAPES[name])
+        if not os.path.exists(path(name, "dnnconf")):
+            synth.write_dnn(path(name), m.cfg.n_states, dc)
+        opts = [o if o != "@DNN@" else path(name, "dnnconf") for o in opts]
     # one short utterance is enough to make the host load everything and call startup()
     rng = np.random.default_rng(5)
-    x, _ = m.sample_utterance(rng, 60)
     fn = path(name, "probe.mfc")
-    synth.write_htk_param(fn, x)
+    if is_dnn:
+        synth.write_htk_param(fn, synth.sample_dnn_input(rng, 60, dc.in_dim), parmkind=synth.PARMKIND_USER)
+    else:
+        synth.write_htk_param(fn, m.sample_utterance(rng, 60)[0])
     env = dict(os.environ, JREF_QUIET="1", JB200_EXPORT=path(name, "model.jb2m"))
     args = [jref, "-dump", path(name, "probe.jrf"), "-plugindir", os.path.join(ROOT, "oracle", "_ref"),
             "-h", os.path.join(mdir, "hmmdefs"), "-hlist", os.path.join(mdir, "hmmlist"),
@@ -96,9 +107,26 @@ def ref_args(name: str) -> list:
     """jconf-style options for running the reference on this workload."""
     preset, opts = WORKLOADS[name]
     mdir = model_dir(name)
+    opts = [o if o != "@DNN@" else path(name, "dnnconf") for o in opts]
     return ["-h", os.path.join(mdir, "hmmdefs"), "-hlist", os.path.join(mdir, "hmmlist"),
             "-v", os.path.join(mdir, "dict"), "-nlr", os.path.join(mdir, "lm.arpa"),
             "-input", "mfcfile", "-1pass"] + opts
+
+
+def is_dnn(name: str) -> bool:
+    return name in DNN_SHAPES
+
+
+def sample_inputs(name: str, m: synth.SynthModel, n_utts: int, n_frames: int, seed: int):
+    """Feature matrices in the layout the workload's acoustic model takes."""
+    if name in DNN_SHAPES:
+        rng = np.random.default_rng(seed)
+        return [synth.sample_dnn_input(rng, n_frames, DNN_SHAPES[name]["in_dim"]) for _ in range(n_utts)]
+    return sample_batch(m, n_utts, n_frames, seed)
+
+
+def write_input(name: str, fn: str, x) -> None:
+    synth.write_htk_param(fn, x, parmkind=synth.PARMKIND_USER if name in DNN_SHAPES else synth.PARMKIND_MFCC_E_D_A)
 
 
 def sample_batch(m: synth.SynthModel, n_utts: int, n_frames: int, seed: int):
