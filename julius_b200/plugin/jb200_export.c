@@ -400,9 +400,7 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
 }
 
 /* ---------------------------------------------------------------- entry: build the blob */
-int jb200_flatten_recog(Recog *recog, jb200_blob *b) {
-  PROCESS_AM *am = recog->amlist;
-  RecogProcess *r = recog->process_list;
+int jb200_flatten(PROCESS_AM *am, RecogProcess *r, jb200_blob *b) {
   CdReg cd;
   int rc = 0;
 
@@ -410,8 +408,6 @@ int jb200_flatten_recog(Recog *recog, jb200_blob *b) {
   pm_init(&cd.map, 4096);
   iv_push(&cd.off, 0);
   if (am == NULL) { jlog("ERROR: jb200: no acoustic model\n"); return -1; }
-  if (am->next != NULL || (r && r->next != NULL))
-    jlog("WARNING: jb200: several AM/SR instances; only the first is flattened\n");
 
   if (am->dnn != NULL) rc = flatten_dnn(am, b);
   else rc = flatten_gmm(am, b);
@@ -434,7 +430,14 @@ int jb200_flatten_recog(Recog *recog, jb200_blob *b) {
   return rc;
 }
 
+int jb200_flatten_recog(Recog *recog, jb200_blob *b) {
+  if (recog->amlist && (recog->amlist->next != NULL || (recog->process_list && recog->process_list->next != NULL)))
+    jlog("WARNING: jb200: several AM/SR instances; only the first is flattened\n");
+  return jb200_flatten(recog->amlist, recog->process_list, b);
+}
+
 /* ---------------------------------------------------------------- plugin ABI */
+#ifndef JB200_NO_PLUGIN_ENTRY
 int initialize(void) { return 0; }
 
 int get_plugin_info(int opcode, char *buf, int buflen) {
@@ -444,19 +447,26 @@ int get_plugin_info(int opcode, char *buf, int buflen) {
   return 0;
 }
 
+extern int jb200_attach(Recog *recog, jb200_blob *b);     /* jb200_attach.c */
+
 int startup(void *data) {
   Recog *recog = (Recog *)data;
   const char *path = getenv("JB200_EXPORT");
-  jb200_blob b;
+  const char *attach = getenv("JB200_ATTACH");
+  jb200_blob *b;
   int rc;
-  if (path == NULL) return 0;
-  jb200_blob_init(&b);
-  rc = jb200_flatten_recog(recog, &b);
-  if (rc == 0) {
-    rc = jb200_blob_save(&b, path);
-    if (rc == 0) jlog("STAT: jb200: flattened model written to %s (%d arrays)\n", path, b.n);
+  if (path == NULL && (attach == NULL || atoi(attach) == 0)) return 0;
+  b = (jb200_blob *)malloc(sizeof(jb200_blob));
+  jb200_blob_init(b);
+  rc = jb200_flatten_recog(recog, b);
+  if (rc == 0 && path != NULL) {
+    rc = jb200_blob_save(b, path);
+    if (rc == 0) jlog("STAT: jb200: flattened model written to %s (%d arrays)\n", path, b->n);
     else jlog("ERROR: jb200: cannot write %s\n", path);
   }
-  jb200_blob_free(&b);
+  if (rc == 0 && attach != NULL && atoi(attach) != 0) return jb200_attach(recog, b);   /* keeps the blob alive */
+  jb200_blob_free(b);
+  free(b);
   return rc;
 }
+#endif /* JB200_NO_PLUGIN_ENTRY */

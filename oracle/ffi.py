@@ -15,6 +15,7 @@ from julius_b200 import desc as D
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle.so")
 JREF = os.path.join(HERE, "_ref", "jref")
+JREF_GPU = os.path.join(HERE, "_ref", "jref_gpu")
 PLUGDIR = os.path.join(HERE, "_ref")
 
 ATOM_DT = np.dtype([("wid", "<i4"), ("begin", "<i4"), ("end", "<i4"),
@@ -105,7 +106,8 @@ def have_ref() -> bool:
 
 
 def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "out.jrf", export: str | None = None,
-            tokens: bool = False, am_args: list | None = None, quiet: bool = True, timeout: int = 3600):
+            tokens: bool = False, am_args: list | None = None, quiet: bool = True, timeout: int = 3600,
+            binary: str | None = None, env_extra: dict | None = None):
     """Run the compiled reference on HTK parameter files; returns (dump path, stdout)."""
     env = dict(os.environ)
     if quiet:
@@ -114,7 +116,9 @@ def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "ou
         env["JREF_TOKENS"] = "1"
     if export:
         env["JB200_EXPORT"] = export
-    args = [JREF, "-dump", os.path.join(workdir, dump), "-plugindir", PLUGDIR]
+    if env_extra:
+        env.update(env_extra)
+    args = [binary or JREF, "-dump", os.path.join(workdir, dump), "-plugindir", PLUGDIR]
     args += am_args if am_args is not None else ["-h", "hmmdefs", "-hlist", "hmmlist"]
     args += ["-v", "dict", "-nlr", "lm.arpa", "-input", "mfcfile", "-1pass", "-outprobout", "/dev/null"]
     args += list(extra_args)

@@ -58,6 +58,9 @@ static void on_pass1_frame(Recog *recog, void *dummy) {
   FSBeam *d = &(r->pass1);
   int j, tn = d->tn;
   if (!g_tokens) return;
+#ifdef JREF_NO_TOKENS
+  return;
+#endif
   /* record: tag, frame, count, then (node, score, last_tre wid, last_tre endtime, last_cword, last_lscore) */
   wi(0x544f4b31); /* 'TOK1' */
   wi(r->am->mfcc->f);

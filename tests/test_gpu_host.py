@@ -1,0 +1,60 @@
+"""GPU: the drop-in boundaries exercised through the UNMODIFIED reference host (oracle/_ref).
+
+  * jref + jb200.jpi with JB200_ATTACH=1: Julius' own pass-1 beam consumes GPU scores written into
+    HMMWork.outprob_cache at CALLBACK_EVENT_PASS1_BEGIN  -> dump must equal the stock run (golden).
+  * jref_gpu: libjulius linked with jb200_beam_shim.o instead of beam.o -> the stock host drives the
+    GPU scorer + GPU beam through get_back_trellis_init/_end/finalize_1st_pass -> same trellis.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from julius_b200 import refdump, synth
+from util import Golden, atoms_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _prepare(case, tmp_path):
+    from oracle import ffi
+    if not (ffi.have_ref() and os.path.exists(ffi.JREF_GPU)):
+        pytest.skip("oracle/_ref host binaries not built")
+    g = Golden(case)
+    d = str(tmp_path)
+    m = synth.SynthModel(synth.SynthConfig.preset(g.meta["preset"]))
+    m.write_all(d)
+    files = []
+    for i, x in enumerate(g.feats):
+        fn = os.path.join(d, f"u{i}.mfc")
+        synth.write_htk_param(fn, x)
+        files.append(fn)
+    return g, d, files
+
+
+@pytest.mark.parametrize("case", ["tiny", "small_b100"])
+def test_attached_gpu_scores_drive_the_stock_beam(case, tmp_path):
+    from oracle import ffi
+    g, d, files = _prepare(case, tmp_path)
+    dump, out = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], env_extra={"JB200_ATTACH": "1"})
+    utts = refdump.load_refdump(dump)
+    assert len(utts) == len(g.utts)
+    for u, ref in zip(utts, g.utts):
+        assert np.array_equal(u.outprob.view(np.uint32), ref.outprob.view(np.uint32))
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+
+
+@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_safe"])
+def test_stock_host_with_gpu_beam_linked_in(case, tmp_path):
+    from oracle import ffi
+    g, d, files = _prepare(case, tmp_path)
+    dump, out = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], binary=ffi.JREF_GPU)
+    utts = refdump.load_refdump(dump)
+    assert len(utts) == len(g.utts)
+    for u, ref in zip(utts, g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.status == ref.status
+        assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
