@@ -156,7 +156,7 @@ def reference_main(a):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_procs = max(1, min(cores, 64))
+    n_procs = max(1, min(cores, 128))
     upp = a.cpu_sample_utts or 2
     # steps are bounded samples of the same workload
     for w in range(min(a.warmup, 1)):
@@ -362,7 +362,7 @@ def product_main(a):
         if world == 1 and not a.no_cpu_baseline:
             try:
                 cores = os.cpu_count() or 1
-                n_procs = max(1, min(cores, 64))
+                n_procs = max(1, min(cores, 128))
                 upp = a.cpu_sample_utts or 2
                 f, s = run_reference_sample(a.workload, n_procs, upp, T, 4242)
                 line["cpu_baseline"] = {"value": f / s, "unit": "frames/s", "cores": n_procs, "kind": "reference",
