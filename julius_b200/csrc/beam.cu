@@ -83,7 +83,7 @@ struct BeamParams {
   long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
   unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
   unsigned long long *outv;          // per-utterance extracted heap roots [beam+1]
-  unsigned long long *misspec_counter; int force_seq_heap, check_heap;
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, heap_mode;
   int maxt, maxc, maxw, maxbits;
 };
 
@@ -296,6 +296,54 @@ __device__ void heap_extract_seq(unsigned long long *A, int n, int extract) {
   __syncthreads();
 }
 
+__device__ __forceinline__ void lds_pair(unsigned addr, unsigned &x0, unsigned &x1, unsigned &y0, unsigned &y1) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void lds_one(unsigned addr, unsigned &x0, unsigned &x1) {
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_one(unsigned addr, unsigned x0, unsigned x1) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(x0), "r"(x1) : "memory");
+}
+
+// Lean single-thread extraction replay: explicit shared-window addressing, one aligned 16-byte load per
+// tree level.  Max-heap selects stop as soon as the larger child is below `lose_below` (see the note on
+// winners and losers above heap_extract_pipelined): ~8.5 instead of ~11.2 levels per extraction.
+template <bool MAXHEAP>
+__device__ void heap_extract_lean(unsigned long long *A, const int n, const int extract, const float lose_below) {
+  if (threadIdx.x == 0) {
+    const unsigned hb = smem_u32(A);
+    int m = n;
+    unsigned r0, r1;
+    lds_one(hb + 8u, r0, r1);                         // current root
+    for (int x = 0; x < extract; x++) {
+      unsigned s_lo, s_hi;
+      lds_one(hb + ((unsigned)m << 3), s_lo, s_hi);
+      sts_one(hb + ((unsigned)m << 3), r0, r1);       // A[m] = A[1]
+      m--;
+      if (m < 1) break;
+      const float sv = __uint_as_float(s_lo);
+      unsigned par = 1u;
+      bool first = true;
+      while (true) {
+        const unsigned child = par << 1;
+        if ((int)child > m) break;
+        unsigned x0, x1, y0, y1;
+        lds_pair(hb + (par << 4), x0, x1, y0, y1);
+        const bool right = ((int)child < m) && hcmp<MAXHEAP>(__uint_as_float(x0), __uint_as_float(y0));
+        const unsigned c_lo = right ? y0 : x0, c_hi = right ? y1 : x1;
+        if (hstop<MAXHEAP>(sv, __uint_as_float(c_lo)) || (MAXHEAP && __uint_as_float(c_lo) < lose_below)) break;
+        sts_one(hb + (par << 3), c_lo, c_hi);
+        if (first) { r0 = c_lo; r1 = c_hi; first = false; }   // new root value
+        par = child + (right ? 1u : 0u);
+      }
+      sts_one(hb + (par << 3), s_lo, s_hi);
+      if (first) { r0 = s_lo; r1 = s_hi; }
+    }
+  }
+  __syncthreads();
+}
+
 // Pipelined extraction replay, warp 0, lock-step.  Lane k of the warp owns the extractions x with
 // x mod NL == k; every extraction in flight advances exactly one tree level per "tick" and a new one
 // starts at least two ticks after the previous one, so extraction x always works two levels above x-1:
@@ -308,11 +356,17 @@ __device__ void heap_extract_seq(unsigned long long *A, int n, int extract) {
 //     get there through the slot's ancestors.  So x does not start while an extraction in flight sits
 //     on an ancestor of slot n-x (a stall of a tick or two, ~0.6 tick per extraction on average);
 //     once no one does, A[n-x] is final.  No speculation, no rollback.
+// Max-heap ("upward") selects only: an element that is not among the `extract` largest can never be
+// extracted, and the order in which the winners come out does not depend on how the losers are
+// arranged among themselves (a loser only ever moves when no winner is below the hole, and a re-inserted
+// loser sinks below every winner whatever its value).  So the sift stops as soon as the larger child is
+// below `lose_below`, any lower bound of the extract-th largest score.
 // A single thread needs ~90 cycles per tree level (dependent-issue latency); the lock-step pipeline
 // retires one extraction every ~2.6 ticks instead of every ~11 levels.
 // (CPU model of exactly this schedule vs the sequential loop: tools/heapsim.cpp.)  Ends with a barrier.
 template <bool MAXHEAP>
-__device__ void heap_extract_pipelined(unsigned long long *A, const int n, const int extract, unsigned long long *outv) {
+__device__ void heap_extract_pipelined(unsigned long long *A, const int n, const int extract, unsigned long long *outv,
+                                       const float lose_below /* max-heap only: children below this never win */) {
   constexpr int NL = 16;
   if (threadIdx.x < 32) {
     const unsigned full = 0xffffffffu;
@@ -331,7 +385,7 @@ __device__ void heap_extract_pipelined(unsigned long long *A, const int n, const
           const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(A + child);
           const bool right = (child < m) && hcmp<MAXHEAP>(hval(pr.x), hval(pr.y));
           const unsigned long long c = right ? pr.y : pr.x;
-          if (!hstop<MAXHEAP>(sv, hval(c))) { stop = false; put = c; }
+          if (!hstop<MAXHEAP>(sv, hval(c)) && !(MAXHEAP && hval(c) < lose_below)) { stop = false; put = c; }
           A[par] = put;
           if (!stop) { par = child + (right ? 1 : 0); lvl++; }
         } else A[par] = put;
@@ -384,7 +438,7 @@ beam_kernel(const BeamParams p) {
   int *poff = offs + (p.beam + 2);                                                // [beam+2] arrival-order bit positions per survivor
   __shared__ int s_warp[NWARP + 1];
   __shared__ int s_ncre, s_E, s_natoms, s_ns, s_cur, s_overflow, s_found, s_flag;
-  __shared__ unsigned s_pmaxkey;
+  __shared__ unsigned s_pmaxkey, s_losekey;
   __shared__ unsigned long long s_webest;
   __shared__ float s_thr;
   __shared__ long long s_outbase;
@@ -680,7 +734,7 @@ beam_kernel(const BeamParams p) {
       nt.score += outprob_style(p, row, p.nodes[node].out, nt.tre_wid);
       tn[r] = nt;
       heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
-      if (p.prune_width >= 0.0f) atomicMax(&s_pmaxkey, fkey(nt.score));
+      atomicMax(&s_pmaxkey, fkey(nt.score));
     };
     if (ncre > 0) {
       for (int c = tid; c < cand_total; c += BEAM_THREADS) {
@@ -713,8 +767,56 @@ beam_kernel(const BeamParams p) {
         ns_new = need;
         bool ok = false;
         if (!p.force_seq_heap) {
-          if (upward) { heap_build<true>(heap, ncre); heap_extract_pipelined<true>(heap, ncre, extract, outv); }
-          else { heap_build<false>(heap, ncre); heap_extract_pipelined<false>(heap, ncre, extract, outv); }
+          if (upward) {
+            // lower bound of the need-th largest score from a 1024-bin histogram of the order-preserving
+            // keys (bin width ~0.5 in score units, adapted to the magnitude of the best score)
+            constexpr int NB = 1024;
+            int *hist = offs;                          // offs/poff are dead after P5
+            const int nb = min(NB, 2 * (p.beam + 2));
+            for (int i = tid; i < nb; i += BEAM_THREADS) hist[i] = 0;
+            __syncthreads();
+            const unsigned maxkey = s_pmaxkey;
+            const int e = (int)((((maxkey & 0x80000000u) ? (maxkey & 0x7fffffffu) : ~maxkey) >> 23) & 0xffu) - 127;
+            const int sh = max(0, min(24, 22 - e));
+            for (int r = tid; r < ncre; r += BEAM_THREADS) {
+              const unsigned key = fkey(hval(heap[r + 1]));
+              const unsigned bin = min((unsigned)(nb - 1), (maxkey - key) >> sh);
+              atomicAdd(&hist[bin], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {
+              int cum = 0, found = -1;
+              for (int b0 = 0; b0 < nb && found < 0; b0 += 32) {
+                const int v = (b0 + tid < nb) ? hist[b0 + tid] : 0;
+                int x = v;
+                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
+                const unsigned hit = __ballot_sync(0xffffffffu, cum + x >= need);
+                if (hit) found = b0 + __ffs(hit) - 1;
+                cum += __shfl_sync(0xffffffffu, x, 31);
+              }
+              if (tid == 0) {
+                unsigned lk = 0u;
+                if (found >= 0 && found < nb - 1) {
+                  const unsigned long long drop = (unsigned long long)(found + 1) << sh;
+                  lk = (drop < maxkey) ? maxkey - (unsigned)drop : 0u;
+                }
+                s_losekey = lk;
+              }
+            }
+            __syncthreads();
+            const unsigned lk = s_losekey;
+            const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
+            heap_build<true>(heap, ncre); PROF_MARK(7);
+            if (p.heap_mode == 0) {
+              heap_extract_lean<true>(heap, ncre, extract, lose_below);
+              for (int k = tid; k < extract; k += BEAM_THREADS) outv[k] = heap[ncre - k];   // same convention as the pipelined replay
+              __syncthreads();
+            } else heap_extract_pipelined<true>(heap, ncre, extract, outv, lose_below);
+          } else {
+            heap_build<false>(heap, ncre); PROF_MARK(7);
+            if (p.heap_mode == 0) heap_extract_lean<false>(heap, ncre, extract, -INFINITY);
+            else heap_extract_pipelined<false>(heap, ncre, extract, outv, -INFINITY);
+          }
           ok = true;
           if (ok) {
             // survivors: upward = the extracted maxima, last extracted first (slots n-need+1..n);
@@ -1044,6 +1146,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMemset(P.misspec_counter, 0, sizeof(unsigned long long)));
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
   P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
+  P.heap_mode = getenv("JB200_HEAP_MODE") ? atoi(getenv("JB200_HEAP_MODE")) : 0;   // 0 lean sequential (+loser cut), 1 lock-step pipelined
+  P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   {
     size_t tot = (size_t)max_utts * n;
     fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.firstseq, P.bestkey, tot);

@@ -6,8 +6,9 @@
 //    gprune_safe.c:75-202, gprune_common.c:41-126, addlog.c:102-123)
 // and for outprob_cd (outprob.c:286-400) in the cd-set kernel.
 //
-// Layout in HBM.  One 16-byte aligned record per Gaussian:
-//      [ m0 iv0 m1 iv1 ... m(D-1) iv(D-1) gconst lnw (pad) ]       (2D+2 floats -> 320 B for D=39)
+// Layout in HBM.  One 16-byte aligned record per Gaussian, in quads so that a 64-bit register pair
+// holds two dimensions for the packed fp32x2 FMA (FFMA2):
+//      [ (m0 m1 iv0 iv1) (m2 m3 iv2 iv3) ... (m38 gconst iv38 lnw) ]   (2D+2 floats -> 320 B for D=39)
 // Records of a state are contiguous and states follow each other, so a tile of states is ONE
 // contiguous byte range that a single 1-D bulk (TMA) copy stages into shared memory
 // (cp.async.bulk + mbarrier, double buffered).  Every thread owns FPT frames whose feature
@@ -34,6 +35,26 @@ static constexpr int GMM_NMAX = 16;            // max -tmix for the pruned varia
 __host__ __device__ constexpr int gmm_stride(int D) { return ((2 * D + 2) + 3) & ~3; }
 
 struct GmmTile { int s0, ns, g0, ng; };
+
+// record layout: quads (m_2q, m_2q+1, iv_2q, iv_2q+1); gconst / lnw ride in the unused halves of the
+// last quad when D is odd, or in an extra quad when D is even.  Same size as interleaving pairs.
+__host__ __device__ constexpr int rec_mean(int d) { return 4 * (d >> 1) + (d & 1); }
+__host__ __device__ constexpr int rec_ivar(int d) { return 4 * (d >> 1) + 2 + (d & 1); }
+__host__ __device__ constexpr int rec_gconst(int D) { return (D & 1) ? 4 * (D >> 1) + 1 : 2 * D; }
+__host__ __device__ constexpr int rec_lnw(int D) { return (D & 1) ? 4 * (D >> 1) + 3 : 2 * D + 1; }
+
+// packed fp32x2 FMA (SASS FFMA2): one issue slot for two lanes' worth of work.  Every use below is an
+// exactly-rounded single operation (a*b+0, a*(-1)+c), so the exact mode stays bit-identical.
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffu)); }
+__device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
 __device__ __forceinline__ float addlog_step_exact(float y, float x, const float *__restrict__ tbl) {
   // addlog.c:112-120
@@ -97,7 +118,8 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
   }
 
   // this thread's frames, in registers
-  float v[GMM_FPT][D];
+  float v[GMM_FPT][D];                       // scalar copy (pruned variant)
+  unsigned long long v2[GMM_FPT][NQ];        // the same, packed (x_2q, x_2q+1) for the FFMA2 path
   int fr[GMM_FPT];
 #pragma unroll
   for (int k = 0; k < GMM_FPT; k++) {
@@ -105,7 +127,10 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
     const float *src = feats + (size_t)min(fr[k], T - 1) * D;
 #pragma unroll
     for (int d = 0; d < D; d++) v[k][d] = __ldg(src + d);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) v2[k][q] = pack2((2 * q < D) ? v[k][2 * q < D ? 2 * q : 0] : 0.0f, (2 * q + 1 < D) ? v[k][2 * q + 1 < D ? 2 * q + 1 : 0] : 0.0f);
   }
+  const unsigned long long NEG1 = pack2(-1.0f, -1.0f), ZERO2 = pack2(0.0f, 0.0f);
 
   for (int ti = tile_begin; ti < tile_end; ti++) {
     const int b = (ti - tile_begin) & 1;
@@ -136,26 +161,35 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
         for (int k = 0; k < GMM_FPT; k++) { y[k] = JB200_LOG_ZERO; ssum[k] = 0.0f; }
         for (int m = nm - 1; m >= 0; m--) {
           const float4 *p = reinterpret_cast<const float4 *>(pb + (size_t)(grel + m) * STRIDE);
-          const float gconst = pb[(size_t)(grel + m) * STRIDE + 2 * D];
-          const float lnw = pb[(size_t)(grel + m) * STRIDE + 2 * D + 1];
+          const float gconst = pb[(size_t)(grel + m) * STRIDE + rec_gconst(D)];
+          const float lnw = pb[(size_t)(grel + m) * STRIDE + rec_lnw(D)];
           float acc[GMM_FPT];
+          unsigned long long acc2[GMM_FPT];
 #pragma unroll
-          for (int k = 0; k < GMM_FPT; k++) acc[k] = gconst;
+          for (int k = 0; k < GMM_FPT; k++) { acc[k] = gconst; acc2[k] = pack2(gconst, 0.0f); }
 #pragma unroll
           for (int q = 0; q < NQ; q++) {
-            const float4 w = p[q];
             const int d0 = 2 * q, d1 = 2 * q + 1;
+            if (d0 < D) {
+              const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(p)[q];     // .x = (m_d0, m_d1)  .y = (iv_d0, iv_d1)
 #pragma unroll
-            for (int k = 0; k < GMM_FPT; k++) {
-              if (d0 < D) {
-                if (EXACT) { float x = __fsub_rn(v[k][d0 < D ? d0 : 0], w.x); acc[k] = __fadd_rn(acc[k], __fmul_rn(__fmul_rn(x, x), w.y)); }
-                else { float x = v[k][d0 < D ? d0 : 0] - w.x; acc[k] = fmaf(x * w.y, x, acc[k]); }
-              }
-              if (d1 < D) {
-                if (EXACT) { float x = __fsub_rn(v[k][d1 < D ? d1 : 0], w.z); acc[k] = __fadd_rn(acc[k], __fmul_rn(__fmul_rn(x, x), w.w)); }
-                else { float x = v[k][d1 < D ? d1 : 0] - w.z; acc[k] = fmaf(x * w.w, x, acc[k]); }
+              for (int k = 0; k < GMM_FPT; k++) {
+                const unsigned long long x2 = fma2(w.x, NEG1, v2[k][q]);           // x = v - m      (exact)
+                if (EXACT) {
+                  const unsigned long long t2 = fma2(fma2(x2, x2, ZERO2), w.y, ZERO2);   // (x*x)*iv, two roundings as the reference
+                  acc[k] = __fadd_rn(acc[k], lo2(t2));                             // tmp += ... in dimension order
+                  if (d1 < D) acc[k] = __fadd_rn(acc[k], hi2(t2));
+                } else {
+                  const unsigned long long xi = fma2(x2, w.y, ZERO2);
+                  if (d1 < D) acc2[k] = fma2(xi, x2, acc2[k]);
+                  else acc[k] = fmaf(lo2(xi), lo2(x2), 0.0f);                      // odd tail dimension
+                }
               }
             }
+          }
+          if (!EXACT) {
+#pragma unroll
+            for (int k = 0; k < GMM_FPT; k++) acc[k] = ((D & 1) ? acc[k] : 0.0f) + lo2(acc2[k]) + hi2(acc2[k]);
           }
           const bool invalid = (gconst != gconst);   // NaN marks a NULL density (gprune_none.c:66)
 #pragma unroll
@@ -189,11 +223,12 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
           int num = 0; float thres = JB200_LOG_ZERO;
           for (int m = 0; m < nm; m++) {
             const float *rec = pb + (size_t)(grel + m) * STRIDE;
-            const float gconst = rec[2 * D];
+            const float gconst = rec[rec_gconst(D)];
             float acc = gconst;
+#pragma unroll
             for (int d = 0; d < D; d++) {
-              float x = __fsub_rn(v[k][d], rec[2 * d]);
-              acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(x, x), rec[2 * d + 1]));
+              float x = __fsub_rn(v[k][d], rec[rec_mean(d)]);
+              acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(x, x), rec[rec_ivar(d)]));
             }
             float sc = (gconst != gconst) ? JB200_LOG_ZERO : acc * -0.5f;
             if (num >= gprune_num && sc <= thres) continue;
@@ -202,7 +237,7 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
           }
           float y = JB200_LOG_ZERO, ssum = 0.0f;
           for (int i = num - 1; i >= 0; i--) {
-            float sc = __fadd_rn(cs[i], pb[(size_t)(grel + ci[i]) * STRIDE + 2 * D + 1]);
+            float sc = __fadd_rn(cs[i], pb[(size_t)(grel + ci[i]) * STRIDE + rec_lnw(D)]);
             if (EXACT) y = addlog_step_exact(y, sc, tbl);
             else { if (sc > y) { ssum = ssum * __expf(y - sc) + 1.0f; y = sc; } else ssum += __expf(sc - y); }
           }
@@ -270,11 +305,11 @@ __global__ void gauss_frame_kernel(const float *__restrict__ pk, int stride, int
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const float *rec = pk + (size_t)g * stride;
-  float gconst = rec[2 * D];
+  float gconst = rec[rec_gconst(D)];
   float acc = gconst;
   for (int d = 0; d < D; d++) {
-    float x = __fsub_rn(feat[d], rec[2 * d]);
-    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(x, x), rec[2 * d + 1]));
+    float x = __fsub_rn(feat[d], rec[rec_mean(d)]);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(x, x), rec[rec_ivar(d)]));
   }
   out[g] = (gconst != gconst) ? JB200_LOG_ZERO : acc * -0.5f;
 }
@@ -345,9 +380,9 @@ extern "C" int jb200_gmm_create(const jb200_gmm_desc *d, int device, int mode, j
   std::vector<float> pk((size_t)h->G * h->stride, 0.0f);
   for (int g = 0; g < h->G; g++) {
     float *rec = &pk[(size_t)g * h->stride];
-    for (int k = 0; k < h->D; k++) { rec[2 * k] = d->mean[(size_t)g * h->D + k]; rec[2 * k + 1] = d->ivar[(size_t)g * h->D + k]; }
-    rec[2 * h->D] = d->valid[g] ? d->gconst[g] : NAN;
-    rec[2 * h->D + 1] = d->lnweight[g];
+    for (int k = 0; k < h->D; k++) { rec[rec_mean(k)] = d->mean[(size_t)g * h->D + k]; rec[rec_ivar(k)] = d->ivar[(size_t)g * h->D + k]; }
+    rec[rec_gconst(h->D)] = d->valid[g] ? d->gconst[g] : NAN;
+    rec[rec_lnw(h->D)] = d->lnweight[g];
   }
   // tiles: consecutive states, <= GMM_TILE_STATES states and <= GMM_TILE_GAUSS Gaussians
   std::vector<GmmTile> tiles;
