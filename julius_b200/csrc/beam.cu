@@ -51,11 +51,11 @@ static constexpr unsigned SEQ_LOCAL = 1u << SEQ_LOCAL_BITS;
 static constexpr int CD_NMAX = 16;
 static constexpr int MAX_WORDS = 150;      // MAXSEQNUM, libsent/include/sent/speech.h:50
 
-struct NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, scid; int out; int pad; };   // 32 B
-struct Tok { float score; int node; int tre; int cword; float lscore; int tre_wid; };              // 24 B
-struct Cand { float score; int node; float lscore; int src; };                                     // 16 B
-struct IsoCand { float score; int e; float lscore; int first_e; };                                 // 16 B
-struct WEnd { int j; int atom; int last_word; float base; int transp2; int nintra; };              // 24 B
+struct __align__(16) NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, scid; int out; int pad; };   // 32 B
+struct __align__(8) Tok { float score; int node; int tre; int cword; float lscore; int tre_wid; };              // 24 B
+struct __align__(16) Cand { float score; int node; float lscore; int src; };                                     // 16 B
+struct __align__(16) IsoCand { float score; int e; float lscore; int first_e; };                                 // 16 B
+struct __align__(8) WEnd { int j; int atom; int last_word; float base; int transp2; int nintra; };              // 24 B
 
 struct BeamParams {
   // tree
