@@ -103,3 +103,27 @@ def test_full_size_heap_self_check(monkeypatch, oracle_lib):
     o = oracle_lib.beam_decode(ds, oracle_lib.gmm_score(ds, x))
     ok, why = atoms_equal(res[0]["atoms"], o["atoms"])
     assert ok, why
+
+
+@pytest.mark.parametrize("name,frames", [("mono100", 400), ("tri20k_gbeam", 250)])
+def test_other_baseline_configs_end_to_end_vs_oracle(name, frames, oracle_lib):
+    """BASELINE.json configs[0] (monophone 16-mix, 100 words) and configs[2] (-gprune beam, which is the
+    safe top-N algorithm for state-tied models): GPU end to end == CPU restatement, atom for atom."""
+    if not workload.ready(name):
+        pytest.skip(f"workloads/{name} not prepared")
+    blob = refdump.load_blob(workload.path(name, "model.jb2m"))
+    ds = desc.Descriptors(blob)
+    m = workload.synth_model(name)
+    am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(ds, am, max_utts=4, max_frames=4 * frames)
+    feats = workload.sample_batch(m, 2, frames, seed=55)
+    res = dec.decode(feats)
+    for x, r in zip(feats, res):
+        sc = oracle_lib.gmm_score(ds, x)
+        got = am.score(x)
+        assert np.array_equal(got.view(np.uint32), sc.view(np.uint32))
+        o = oracle_lib.beam_decode(ds, sc)
+        assert r["overflow"] == 0
+        ok, why = atoms_equal(r["atoms"], o["atoms"])
+        assert ok, why
+        assert r["words"] == o["words"] and r["status"] == o["status"]
