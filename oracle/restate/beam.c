@@ -17,7 +17,8 @@
  *   bi_prob_*                                libsent/src/ngram/ngram_access.c:249-466
  *   bt_relocate_rw / bt_sort_rw              libjulius/src/backtrellis.c:218-267, 438-478
  * for the stock "fast" build switches (UNIGRAM_FACTORING, LOWMEM2, PASS1_IWCD,
- * SCORE_PRUNING, no WPAIR/WORD_GRAPH), N-gram LM, non-multipath HMMs.
+ * SCORE_PRUNING, no WPAIR/WORD_GRAPH), N-gram LM; both the NORMAL (:2838-2894) and the MULTIPATH
+ * (:2752-2828, forced by -multipath or needed by the HMM topology) branches.
  * Sequential, same visiting order, same fp32 expression order.
  */
 #include <math.h>
@@ -273,6 +274,15 @@ static int save_trellis(Beam *b, const Tok *tk, int t) {
   return b->natoms++;
 }
 
+/* multipath: the root node has no output, go one step further (beam.c:2467-2500, :2584-2605) */
+static void propagate_from_root(Beam *b, int root, float tmpsum, int tre, int last_word, float lsc) {
+  const jb200_tree_desc *t = b->t;
+  int k;
+  if (t->self_a[root] != JB200_LOG_ZERO) propagate_token(b, root, tmpsum + t->self_a[root], tre, last_word, lsc);
+  if (t->next_a[root] != JB200_LOG_ZERO) propagate_token(b, root + 1, tmpsum + t->next_a[root], tre, last_word, lsc);
+  for (k = t->arc_off[root]; k < t->arc_off[root + 1]; k++) propagate_token(b, t->arc_to[k], tmpsum + t->arc_a[k], tre, last_word, lsc);
+}
+
 static void beam_inter_word(Beam *b, const Tok *tk, int tre) {
   const jb200_tree_desc *t = b->t;
   int node = tk->node, sword = t->stend[node], i, last_word;
@@ -282,7 +292,7 @@ static void beam_inter_word(Beam *b, const Tok *tk, int tre) {
   last_word = transp_s ? tk->last_cword : sword;
   if (sword == t->tail_silwid) return;
   tmpprob = tk->score;
-  tmpprob += t->wordend_a[sword];
+  if (!t->multipath) tmpprob += t->wordend_a[sword];
   if (b->wordend_best_score < tmpprob) {
     b->wordend_best_score = tmpprob; b->wordend_best_node = node;
     b->wordend_best_tre = tre; b->wordend_best_last_cword = tk->last_cword;
@@ -290,13 +300,15 @@ static void beam_inter_word(Beam *b, const Tok *tk, int tre) {
   iwparray = max_successor_prob_iw(b, transp_s ? tk->last_cword : sword);
   for (i = 0; i < t->n_iso; i++) {
     int next_node = t->iso_node[i];
+    if (t->multipath && t->wordbegin[t->head_silwid] == next_node) continue;   /* beam.c:2337-2342 */
     tmpprob = iwparray[t->iso_id[i]];
     tmpsum = tk->score;
-    tmpsum += t->wordend_a[sword];
+    if (!t->multipath) tmpsum += t->wordend_a[sword];
     ngram_score_cache = tmpprob * t->lm_weight + t->lm_penalty;
     tmpsum += ngram_score_cache;
     if (transp_s && tk->last_cword >= 0 && t->is_transparent[tk->last_cword]) tmpsum += t->lm_penalty_trans;
-    propagate_token(b, next_node, tmpsum, tre, last_word, ngram_score_cache);
+    if (t->multipath) propagate_from_root(b, next_node, tmpsum, tre, last_word, ngram_score_cache);
+    else propagate_token(b, next_node, tmpsum, tre, last_word, ngram_score_cache);
   }
 }
 
@@ -314,7 +326,8 @@ static void beam_inter_word_factoring(Beam *b) {
     tmpsum += ngram_score_cache;
     if (transp_s && b->wordend_best_last_cword >= 0 && t->is_transparent[b->wordend_best_last_cword]) tmpsum += t->lm_penalty_trans;
     if (tmpsum < b->score_pruning_threshold) continue;
-    propagate_token(b, next_node, tmpsum, b->wordend_best_tre, last_word, ngram_score_cache);
+    if (t->multipath) propagate_from_root(b, next_node, tmpsum, b->wordend_best_tre, last_word, ngram_score_cache);
+    else propagate_token(b, next_node, tmpsum, b->wordend_best_tre, last_word, ngram_score_cache);
   }
 }
 
@@ -331,7 +344,8 @@ static void init_frame0(Beam *b) {
   else nw->last_lscore = 0.0;
   nw->last_lscore = nw->last_lscore * t->lm_weight + t->lm_penalty;
   nw->last_tre = -1; nw->last_cword = -1;
-  nw->score = outprob_style(b, node, -1, 0) + nw->last_lscore;
+  if (t->multipath) nw->score = nw->last_lscore;      /* beam.c:1654-1656: the word-begin node has no output */
+  else nw->score = outprob_style(b, node, -1, 0) + nw->last_lscore;
   b->token[node] = newid; nw->node = node;
   sort_token_no_order(b, t->beam_width, &b->n_start, &b->n_end);
   b->score_pruning_threshold = JB200_LOG_ZERO;
@@ -371,6 +385,47 @@ static int proceed(Beam *b, int t) {
   return b->tnum[tn] != 0;
 }
 
+/* MULTIPATH MODE, beam.c:2752-2828 + :2935-2941 */
+static int proceed_multipath(Beam *b, int t, int final) {
+  const jb200_tree_desc *tr = b->t;
+  int j, tl, tn;
+  b->tl = b->tn; b->tn = (b->tn == 0) ? 1 : 0;
+  tl = b->tl; tn = b->tn;
+  b->wordend_best_score = JB200_LOG_ZERO;
+  for (j = 0; j < b->tnum[tl]; j++) b->token[b->tlist[tl][j].node] = -1;
+  for (j = b->n_start; j <= b->n_end; j++) {
+    Tok tk = b->tlist[tl][b->tindex[tl][j]];
+    if (tk.score <= JB200_LOG_ZERO) continue;
+    if (tk.score < b->score_pruning_threshold) continue;
+    beam_intra_word(b, j);
+  }
+  sort_token_no_order(b, tr->beam_width, &b->n_start, &b->n_end);
+  for (j = b->n_start; j <= b->n_end; j++) {
+    Tok tk = b->tlist[tn][b->tindex[tn][j]];
+    if (tk.score < b->score_pruning_threshold) continue;
+    if (tr->stend[tk.node] >= 0) {
+      int tre = save_trellis(b, &tk, t);
+      if (final) continue;
+      beam_inter_word(b, &tk, tre);
+    }
+  }
+  if (b->wordend_best_score > JB200_LOG_ZERO) beam_inter_word_factoring(b);
+  b->score_pruning_max = JB200_LOG_ZERO;
+  if (!final) {
+    for (j = 0; j < b->tnum[tn]; j++) {
+      Tok *tk = &b->tlist[tn][b->tindex[tn][j]];
+      if (tr->outstyle[tk->node] == 255) continue;
+      tk->score += outprob_style(b, tk->node, atom_wid(b, tk->last_tre), t);
+      if (b->score_pruning_max < tk->score) b->score_pruning_max = tk->score;
+    }
+  }
+  if (tr->score_pruning_width >= 0.0) b->score_pruning_threshold = b->score_pruning_max - tr->score_pruning_width;
+  else b->score_pruning_threshold = JB200_LOG_ZERO;
+  b->tnum[tl] = 0;
+  sort_token_no_order(b, tr->beam_width, &b->n_start, &b->n_end);
+  return b->tnum[tn] != 0;
+}
+
 static int cmp_atom_idx(const void *pa, const void *pb, void *ctx) {
   const oracle_atom *a = (const oracle_atom *)ctx;
   int x = *(const int *)pa, y = *(const int *)pb;
@@ -386,7 +441,6 @@ int oracle_beam_decode(const jb200_tree_desc *t, const jb200_gmm_desc *g,
   Beam b; int f, i, j, k, framelen, C = g ? g->n_cdsets : 0;
   int *order, *newidx, nkeep;
   memset(&b, 0, sizeof(b));
-  if (t->multipath) return -2;
   b.t = t; b.g = g; b.st = st; b.T = T; b.S = S;
   b.maxtnum = t->beam_width * 2 + t->n_start + 16;
   for (k = 0; k < 2; k++) {
@@ -407,17 +461,23 @@ int oracle_beam_decode(const jb200_tree_desc *t, const jb200_gmm_desc *g,
   framelen = T;
   if (T > 0) {
     init_frame0(&b);
+    if (t->multipath) proceed_multipath(&b, 0, 0);            /* pass1.c:239-242 */
     if (trace_counts) { trace_counts[0] = b.tnum[b.tn]; trace_counts[1] = b.n_end - b.n_start + 1; }
     for (f = 1; f < T; f++) {
-      int alive = proceed(&b, f);
+      int alive = t->multipath ? proceed_multipath(&b, f, 0) : proceed(&b, f);
       if (trace_counts) { trace_counts[2 * f] = b.tnum[b.tn]; trace_counts[2 * f + 1] = b.n_end - b.n_start + 1; }
       if (!alive) { framelen = f; break; }   /* pass1.c:242-245: search terminated */
     }
-    /* get_back_trellis_end (normal version), beam.c:3076-3086 */
-    b.tl = b.tn; b.tn = (b.tn == 0) ? 1 : 0;
-    for (j = b.n_start; j <= b.n_end; j++) {
-      Tok *tk = &b.tlist[b.tl][b.tindex[b.tl][j]];
-      if (t->stend[tk->node] >= 0) save_trellis(&b, tk, T);
+    if (t->multipath) {
+      /* get_back_trellis_end, multipath version (beam.c:3066-3072): only arcs to word ends */
+      proceed_multipath(&b, T, 1);
+    } else {
+      /* get_back_trellis_end (normal version), beam.c:3076-3086 */
+      b.tl = b.tn; b.tn = (b.tn == 0) ? 1 : 0;
+      for (j = b.n_start; j <= b.n_end; j++) {
+        Tok *tk = &b.tlist[b.tl][b.tindex[b.tl][j]];
+        if (t->stend[tk->node] >= 0) save_trellis(&b, tk, T);
+      }
     }
   }
 

@@ -1,7 +1,7 @@
 """Regenerate the committed golden fixtures by running the UNMODIFIED compiled reference
 (oracle/_ref/jref, built by oracle/Makefile from /root/reference) on seeded synthetic models.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 
 Each fixture directory holds
     model.jb2m  the reference's loaded models, flattened by the export plugin
@@ -29,6 +29,8 @@ CASES = {
     "tiny": ("tiny", 2, 150, 0, []),
     "small_b100": ("small", 2, 200, 1, ["-b", "100"]),
     "small_safe": ("small", 1, 150, 0, ["-gprune", "safe", "-tmix", "2", "-b", "60", "-iwcd1", "max"]),
+    # multipath tree (non-emitting word-begin/word-end nodes), beam.c:2752-2828
+    "small_mp": ("small", 2, 200, 1, ["-multipath", "-b", "120"]),
 }
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {
@@ -38,7 +40,10 @@ DNN_CASES = {
 
 def main():
     ffi.build()
+    only = set(sys.argv[1:])
     for name, (preset, nu, nf, nn, extra) in CASES.items():
+        if only and name not in only:
+            continue
         tmp = tempfile.mkdtemp(prefix="jb200_golden_")
         m, files, dump, out = fixtures.make_fixture(preset, tmp, n_utts=nu, n_frames=nf, noise_utts=nn, extra_args=extra)
         dst = os.path.join(HERE, name)
@@ -52,6 +57,8 @@ def main():
         shutil.rmtree(tmp)
         print(name, "->", dst)
     for name, (preset, dkw, nu, nf, extra) in DNN_CASES.items():
+        if only and name not in only:
+            continue
         tmp = tempfile.mkdtemp(prefix="jb200_golden_")
         cfg = synth.SynthConfig.preset(preset)
         m = synth.SynthModel(cfg)

@@ -7,7 +7,7 @@ from julius_b200 import desc, refdump
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["tiny", "small_b100", "small_safe"]
+CASES = ["tiny", "small_b100", "small_safe", "small_mp"]
 
 
 class Golden:
