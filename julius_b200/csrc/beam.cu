@@ -3,7 +3,8 @@
 // Stands in for libjulius/src/beam.c get_back_trellis_init/_proceed/_end + finalize_1st_pass
 // (:1825, :2663, :3052, :3133), outprob_style (outprob_style.c:354-494), the factoring look-ups
 // (factoring_sub.c:942-1143, ngram_access.c:249-305) and the word-trellis store/sort
-// (backtrellis.c:190-267,438-478), for N-gram LMs, non-multipath HMMs, stock "fast" switches.
+// (backtrellis.c:190-267,438-478), for N-gram LMs, stock "fast" switches; normal trees (beam_kernel) and
+// multipath trees (beam_kernel_mp).
 //
 // Why this is not a transliteration.  The reference walks the survivors of frame t-1 one by one
 // and lets each arc "propagate" into a per-node slot; ties are won by whoever arrived first, new
@@ -63,6 +64,10 @@ struct BeamParams {
   const int *rset_ctx; const int *word_ctx; int n_ctx;
   const int *iso_node; const int *iso_id; int n_iso; const float *iw;
   const int *shared_node; const float *shared_f; int n_shared;
+  // multipath trees: the roots carry no output, so cross-word transitions land one arc further
+  // (beam.c:2467-2500, :2584-2605): the successors of the isolated / shared roots, root-major
+  int multipath; const int *isoarc_node; const int *isoarc_iso; const float *isoarc_a; int n_isoarc;
+  const int *sharc_node; const int *sharc_shared; const float *sharc_a; int n_sharc;
   const float *wordend_a; const uint8_t *is_transp; const int *wton; const float *cprob;
   const float *fscore; const int *scword;
   const float *uni_prob; const float *uni_bow; const int *bi_bgn; const int *bi_num; const int *bi_wid; const float *bi_prob;
@@ -419,6 +424,77 @@ __device__ void heap_extract_pipelined(unsigned long long *A, const int n, const
 
 // phase cycle accounting (thread 0 only; negligible cost)
 #define PROF_MARK(k) do { if (tid == 0) { long long _n = clock64(); s_prof[k] += _n - s_tprev; s_tprev = _n; } } while (0)
+
+// finalize_1st_pass (bt_relocate_rw + bt_sort_rw, backtrellis.c:218-267,438-478) + find_1pass_result
+// (beam.c:394-424, :253-301); shared by the normal and the multipath kernel.  All threads call it.
+__device__ __forceinline__ void finalize_utt(const BeamParams &p, const int u, const int tid, const int T, jb200_atom *araw, int *newidx,
+                                             const int *group0, jb200_utt_result *res, int *words,
+                                             int &s_natoms, int &s_overflow, int &s_found, long long &s_outbase,
+                                             long long *s_prof, long long &s_tprev) {
+  // ================= finalize_1st_pass: bt_relocate_rw + bt_sort_rw (backtrellis.c:218-267,438-478) ====
+  // group g = atoms with end frame g (raw atoms are grouped by creation frame already);
+  // inside a group order by word id (unique per group in this build: one token per node).
+  const int natoms = s_natoms;
+  for (int a = tid; a < natoms; a += BEAM_THREADS) {
+    const jb200_atom me = araw[a];
+    const int lo = group0[me.endtime], hi = group0[me.endtime + 1];
+    int rank = 0;
+    for (int b = lo; b < hi; b++) rank += (araw[b].wid < me.wid) ? 1 : 0;
+    newidx[a] = lo + rank;
+  }
+  if (tid == 0) {
+    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
+    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
+    else s_outbase = (long long)base;
+  }
+  __syncthreads();
+  const long long ob = s_outbase;
+  const bool can_write = (ob >= 0);
+  const int kept = can_write ? natoms : 0;
+  for (int a = tid; a < kept; a += BEAM_THREADS) {
+    jb200_atom me = araw[a];
+    me.last = (me.last < 0) ? -1 : newidx[me.last];
+    p.atoms_out[ob + newidx[a]] = me;
+    // find_1pass_result (beam.c:394-424): the latest end frame holding a </s> atom
+    if (me.wid == p.tail_silwid && me.backscore > JB200_LOG_ZERO) atomicMax(&s_found, me.endtime);
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  if (tid == 0) {
+    int status = 0, nw = 0; float score = 0.0f;
+    const int last_time = s_found;
+    if (kept == 0 || last_time < 0) status = -1;
+    else {
+      // the unique </s> atom of group last_time
+      const int lo = group0[last_time], hi = group0[last_time + 1];
+      int best = -1;
+      for (int b = lo; b < hi; b++) {
+        const jb200_atom x = p.atoms_out[ob + b];
+        if (x.wid == p.tail_silwid && x.backscore > JB200_LOG_ZERO) { best = b; break; }
+      }
+      if (best < 0) status = -1;
+      else {
+        // trace_backptr (beam.c:253-301)
+        int tmp[MAX_WORDS]; int n = 0; int a = best;
+        tmp[n++] = p.atoms_out[ob + a].wid;
+        while (p.atoms_out[ob + a].begintime > 0) {
+          a = p.atoms_out[ob + a].last;
+          if (a < 0 || n >= MAX_WORDS) break;
+          tmp[n++] = p.atoms_out[ob + a].wid;
+        }
+        for (int i = 0; i < n; i++) words[i] = tmp[n - i - 1];
+        nw = n; score = p.atoms_out[ob + best].backscore;
+      }
+    }
+    jb200_utt_result r;
+    r.status = status; r.n_frames = T; r.n_atoms = kept; r.n_words = nw; r.score = score;
+    r.atom_offset = ob; r.word_offset = u * MAX_WORDS; r.overflow = s_overflow;
+    *res = r;
+    PROF_MARK(7);
+    if (p.prof) for (int k = 0; k < 8; k++) p.prof[(size_t)u * 8 + k] = s_prof[k];
+  }
+}
 
 // ---- the kernel ------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char beam_smem[];
@@ -894,69 +970,536 @@ beam_kernel(const BeamParams p) {
     __syncthreads();
   }
 
-  // ================= finalize_1st_pass: bt_relocate_rw + bt_sort_rw (backtrellis.c:218-267,438-478) ====
-  // group g = atoms with end frame g (raw atoms are grouped by creation frame already);
-  // inside a group order by word id (unique per group in this build: one token per node).
-  const int natoms = s_natoms;
-  for (int a = tid; a < natoms; a += BEAM_THREADS) {
-    const jb200_atom me = araw[a];
-    const int lo = group0[me.endtime], hi = group0[me.endtime + 1];
-    int rank = 0;
-    for (int b = lo; b < hi; b++) rank += (araw[b].wid < me.wid) ? 1 : 0;
-    newidx[a] = lo + rank;
-  }
-  if (tid == 0) {
-    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
-    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
-    else s_outbase = (long long)base;
-  }
-  __syncthreads();
-  const long long ob = s_outbase;
-  const bool can_write = (ob >= 0);
-  const int kept = can_write ? natoms : 0;
-  for (int a = tid; a < kept; a += BEAM_THREADS) {
-    jb200_atom me = araw[a];
-    me.last = (me.last < 0) ? -1 : newidx[me.last];
-    p.atoms_out[ob + newidx[a]] = me;
-    // find_1pass_result (beam.c:394-424): the latest end frame holding a </s> atom
-    if (me.wid == p.tail_silwid && me.backscore > JB200_LOG_ZERO) atomicMax(&s_found, me.endtime);
-  }
-  __threadfence_block();
+  finalize_utt(p, u, tid, T, araw, newidx, group0, res, words, s_natoms, s_overflow, s_found, s_outbase, s_prof, s_tprev);
+}
+
+// ---- the multipath kernel ----------------------------------------------------------------------------
+// get_back_trellis_proceed, MULTIPATH branch (beam.c:2752-2828, :2930-2941).  Trees of multipath models
+// carry non-emitting word-begin / word-end nodes, and a frame runs in two halves:
+//   A  word-internal transitions of the survivors of t-1 (no output probability yet), then the beam cut
+//      (heap select #1) on the bare transition scores;
+//   B  the word-end tokens among THOSE survivors are stored as trellis words and expanded across words
+//      into the same frame's token set (onto the successors of the roots); then the output probabilities
+//      of all emitting tokens are added and the beam is cut again (heap select #2).
+// Select #2 runs on the token index array exactly as select #1 left it (remaining heap + extracted tail)
+// with the tokens of half B appended, so select #1 is replayed in full, in place -- no loser cut there.
+// Half B reuses the per-node slots: a token made in half A keeps the slot with firstseq = id - 2^30 (< 0:
+// "exists") and bestkey = (score, seq 0), so later arrivals only replace its content when strictly better.
+template <bool MAXHEAP>
+__device__ __forceinline__ int select_exact(unsigned long long *heap, int n, int need, int *ordn) {
+  // sort_token_no_order (beam.c:1492-1520), replayed in place; returns the first survivor's slot
+  heap_build<MAXHEAP>(heap, n);
+  heap_extract_lean<MAXHEAP>(heap, n, MAXHEAP ? need : n - need, -INFINITY);
+  const int start = MAXHEAP ? n - need : 0;
+  for (int k = threadIdx.x; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[start + k + 1] >> 32);
+  return start;
+}
+
+static constexpr int TOK_EXISTS = 0x40000000;
+
+__global__ void __launch_bounds__(BEAM_THREADS, JB200_BEAM_MINBLOCKS)
+beam_kernel_mp(const BeamParams p) {
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
+  const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
+
+  unsigned long long *heap = reinterpret_cast<unsigned long long *>(beam_smem);
+  int *offs = reinterpret_cast<int *>(heap + MAXT + 4);
+  int *hist = offs;                                                               // reused by select #2
+  __shared__ int s_warp[NWARP + 1];
+  __shared__ int s_E, s_natoms, s_ns, s_cur, s_overflow, s_found;
+  __shared__ unsigned s_pmaxkey, s_hmaxkey, s_losekey;
+  __shared__ unsigned long long s_webest;
+  __shared__ float s_thr;
+  __shared__ long long s_outbase;
+  __shared__ long long s_prof[8], s_tprev;
+
+  Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
+  int *ord0 = p.order + (size_t)u * 2 * MAXT;
+  int *firstseq = p.firstseq + (size_t)u * p.n_nodes;
+  unsigned long long *bestkey = p.bestkey + (size_t)u * p.n_nodes;
+  Cand *cand = p.cand + (size_t)u * MAXC;
+  IsoCand *iso = p.iso + (size_t)u * max(max(p.n_iso, p.n_isoarc), 1);
+  WEnd *wend = p.wend + (size_t)u * MAXW;
+  unsigned *bits = p.bitmask + (size_t)u * (p.maxbits >> 5);
+  int *wpre = p.wordpre + (size_t)u * (p.maxbits >> 5);
+  unsigned long long *outv = p.outv + (size_t)u * (p.beam + 1);
+  const long long a0 = p.atom_off[u];
+  const int atom_cap = (int)(p.atom_off[u + 1] - a0);
+  jb200_atom *araw = p.atoms_raw + a0;
+  int *newidx = p.newidx + a0;
+  int *group0 = p.group0 + (size_t)f_begin + u;
+  int *counts = p.counts + (size_t)f_begin * 2;
+  jb200_utt_result *res = p.results + u;
+  int *words = p.words + (size_t)u * MAX_WORDS;
+
+  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1;
+                  for (int k = 0; k < 8; k++) s_prof[k] = 0; s_tprev = clock64(); }
   __syncthreads();
 
-  if (tid == 0) {
-    int status = 0, nw = 0; float score = 0.0f;
-    const int last_time = s_found;
-    if (kept == 0 || last_time < 0) status = -1;
-    else {
-      // the unique </s> atom of group last_time
-      const int lo = group0[last_time], hi = group0[last_time + 1];
-      int best = -1;
-      for (int b = lo; b < hi; b++) {
-        const jb200_atom x = p.atoms_out[ob + b];
-        if (x.wid == p.tail_silwid && x.backscore > JB200_LOG_ZERO) { best = b; break; }
-      }
-      if (best < 0) status = -1;
-      else {
-        // trace_backptr (beam.c:253-301)
-        int tmp[MAX_WORDS]; int n = 0; int a = best;
-        tmp[n++] = p.atoms_out[ob + a].wid;
-        while (p.atoms_out[ob + a].begintime > 0) {
-          a = p.atoms_out[ob + a].last;
-          if (a < 0 || n >= MAX_WORDS) break;
-          tmp[n++] = p.atoms_out[ob + a].wid;
+  // init_nodescore (beam.c:1631-1665): the word-begin node of <s> has no output (:1654-1656)
+  if (T > 0 && tid == 0) {
+    const int node = p.head_node;
+    const NodeRec nr = p.nodes[node];
+    Tok tk;
+    float ll = (nr.scid != 0) ? max_successor_prob(p, -1, nr.scid) : 0.0f;
+    ll = ll * p.lm_weight + p.lm_penalty;
+    tk.lscore = ll; tk.tre = -1; tk.cword = -1; tk.tre_wid = -1; tk.node = node; tk.score = ll;
+    tok0[0] = tk;
+    ord0[0] = 0;
+    s_ns = 1;
+  }
+  __syncthreads();
+
+  int tnum_prev = (T > 0) ? 1 : 0;
+  int groups = T;
+  int n_left = 0;             // tokens of the unfinished (final) frame whose node slots are still set
+
+  // frames 0..T-1 (pass1.c:239-245 calls proceed(0) right after init), then proceed(T, final) (beam.c:3066-3072)
+  for (int t = 0; t <= T && T > 0; t++) {
+    const bool final = (t == T);
+    const int cur = s_cur, nxt = cur ^ 1;
+    Tok *tl = tok0 + (size_t)cur * MAXT, *tn = tok0 + (size_t)nxt * MAXT;
+    int *ordl = ord0 + (size_t)cur * MAXT, *ordn = ord0 + (size_t)nxt * MAXT;
+    const int ns = s_ns;
+    const float thr = s_thr;
+    const float *row = p.rows + (size_t)(f_begin + (final ? 0 : t)) * p.row_stride;
+
+    // ---- P0: clear_tokens
+    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+      const int node = tl[i].node;
+      __stcg(firstseq + node, 0x7fffffff);
+      __stcg(bestkey + node, 0ull);
+    }
+    if (tid == 0) { s_webest = 0ull; s_pmaxkey = fkey(JB200_LOG_ZERO); s_hmaxkey = 0u; if (t > 0) group0[t - 1] = s_natoms; }
+    __syncthreads();
+    PROF_MARK(0);
+
+    // ---- A1: candidate counts per survivor
+    int cand_total;
+    {
+      int carry_c = 0;
+      for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
+        const int j = j0 + tid;
+        int nin = 0;
+        if (j < ns) {
+          const Tok tk = tl[ordl[j]];
+          const NodeRec nr = p.nodes[tk.node];
+          if ((tk.score > JB200_LOG_ZERO) && !(tk.score < thr))
+            nin = (nr.self_a != JB200_LOG_ZERO) + (nr.next_a != JB200_LOG_ZERO) + nr.arc_n;
         }
-        for (int i = 0; i < n; i++) words[i] = tmp[n - i - 1];
-        nw = n; score = p.atoms_out[ob + best].backscore;
+        int tot_c;
+        const int oc = block_excl_scan(nin, s_warp, &tot_c);
+        if (j < ns) offs[j] = carry_c + oc;
+        carry_c += tot_c;
+      }
+      cand_total = carry_c;
+      if (tid == 0) offs[ns] = carry_c;
+      if (cand_total > MAXC || cand_total > p.maxbits) { if (tid == 0) s_overflow = 1; cand_total = 0; }
+    }
+    int nwords = (cand_total + 31) >> 5;
+    for (int w = tid; w < nwords; w += BEAM_THREADS) bits[w] = 0u;
+    __syncthreads();
+    PROF_MARK(1);
+
+    // ---- A2: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177)
+    if (cand_total > 0) {
+      for (int j = tid; j < ns; j += BEAM_THREADS) {
+        const int c0 = offs[j], nin = offs[j + 1] - c0;
+        if (nin == 0) continue;
+        const Tok tk = tl[ordl[j]];
+        const NodeRec nr = p.nodes[tk.node];
+        int k = 0;
+        for (int a = -2; a < nr.arc_n; a++) {
+          int next; float pa;
+          if (a == -2) { if (nr.self_a == JB200_LOG_ZERO) continue; next = tk.node; pa = nr.self_a; }
+          else if (a == -1) { if (nr.next_a == JB200_LOG_ZERO) continue; next = tk.node + 1; pa = nr.next_a; }
+          else { next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
+          float tmpsum = tk.score + pa;
+          float lsc = JB200_LOG_ZERO;
+          if (next != tk.node) {
+            const int scid = p.nodes[next].scid;
+            if (scid != 0) {
+              lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
+              tmpsum -= tk.lscore;
+              tmpsum += lsc;
+            }
+          }
+          if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
+          Cand c; c.score = tmpsum; c.node = next; c.lscore = lsc; c.src = j;
+          cand[c0 + k] = c;
+          if (tmpsum > JB200_LOG_ZERO) {
+            const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
+            cand_atomics(firstseq, bestkey, next, tmpsum, seq, seq);
+          }
+          k++;
+        }
       }
     }
-    jb200_utt_result r;
-    r.status = status; r.n_frames = T; r.n_atoms = kept; r.n_words = nw; r.score = score;
-    r.atom_offset = ob; r.word_offset = u * MAX_WORDS; r.overflow = s_overflow;
-    *res = r;
-    PROF_MARK(7);
-    if (p.prof) for (int k = 0; k < 8; k++) p.prof[(size_t)u * 8 + k] = s_prof[k];
+    __syncthreads();
+    PROF_MARK(2);
+
+    // ---- A3: creators, in arrival order = candidate order
+    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
+      const Cand cd = cand[c];
+      if (!(cd.score > JB200_LOG_ZERO)) continue;
+      const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)(c - offs[cd.src]);
+      if ((unsigned)__ldcg(firstseq + cd.node) == seq) atomicOr(bits + (c >> 5), 1u << (c & 31));
+    }
+    __syncthreads();
+    PROF_MARK(3);
+    int ncre_a;
+    {
+      int carry = 0;
+      for (int w0 = 0; w0 < nwords; w0 += BEAM_THREADS) {
+        const int w = w0 + tid;
+        const int cnt = (w < nwords) ? __popc(__ldcg(bits + w)) : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt, s_warp, &tot);
+        if (w < nwords) wpre[w] = carry + ex;
+        carry += tot;
+      }
+      ncre_a = carry;
+    }
+    if (ncre_a > MAXT) { if (tid == 0) s_overflow = 1; ncre_a = 0; }
+    __syncthreads();
+    PROF_MARK(4);
+
+    // ---- A4: materialise the tokens of half A (no output probability yet) and mark their slots "exists"
+    for (int c = tid; c < cand_total && ncre_a > 0; c += BEAM_THREADS) {
+      const unsigned wbits = __ldcg(bits + (c >> 5));
+      if (!((wbits >> (c & 31)) & 1u)) continue;
+      const int r = wpre[c >> 5] + __popc(wbits & ((1u << (c & 31)) - 1u));
+      const int node = cand[c].node;
+      const unsigned long long bk = __ldcg(bestkey + node);
+      const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
+      const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
+      const Cand cd = cand[offs[j] + local];
+      const Tok src = tl[ordl[j]];
+      Tok nt; nt.node = node;
+      nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = src.tre; nt.cword = src.cword; nt.tre_wid = src.tre_wid;
+      tn[r] = nt;
+      heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
+      __stcg(firstseq + node, r - TOK_EXISTS);
+      __stcg(bestkey + node, ((unsigned long long)fkey(nt.score) << 32) | 0xffffffffull);
+    }
+    __syncthreads();
+    PROF_MARK(5);
+
+    // ---- A5: heap select #1, replayed in full
+    int ns_a;
+    {
+      const int need = p.beam;
+      if (need >= ncre_a) {
+        ns_a = ncre_a;
+        for (int k = tid; k < ns_a; k += BEAM_THREADS) ordn[k] = k;
+      } else {
+        ns_a = need;
+        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn);
+        else select_exact<false>(heap, ncre_a, need, ordn);
+      }
+    }
+    __syncthreads();
+    PROF_MARK(6);
+
+    // ---- B1: word ends among the survivors of select #1: trellis words (save_trellis, beam.c:2209)
+    //          and the cross-word sources (beam_inter_word's per-token part, beam.c:2271-2335)
+    int nbits_b;
+    {
+      int carry_a = s_natoms, carry_w = 0;
+      for (int k0 = 0; k0 < ns_a; k0 += BEAM_THREADS) {
+        const int k = k0 + tid;
+        int is_we = 0, is_tr = 0;
+        Tok tk; NodeRec nr;
+        if (k < ns_a) {
+          tk = tn[ordn[k]];
+          nr = p.nodes[tk.node];
+          if (!(tk.score < thr) && nr.stend >= 0) { is_we = 1; is_tr = (!final && nr.stend != p.tail_silwid); }
+        }
+        int tot_a, tot_w;
+        const int oa = block_excl_scan(is_we, s_warp, &tot_a);
+        const int ow = block_excl_scan(is_tr, s_warp, &tot_w);
+        if (is_we) {
+          const int ai = carry_a + oa;
+          if (ai < atom_cap && t > 0) {
+            jb200_atom a;
+            a.wid = nr.stend; a.backscore = tk.score;
+            a.begintime = (tk.tre < 0 ? -1 : araw[tk.tre].endtime) + 1;
+            a.endtime = t - 1; a.last = tk.tre; a.lscore = tk.lscore;
+            araw[ai] = a;
+          } else s_overflow = 1;
+          if (is_tr) {
+            const int wi = carry_w + ow;
+            if (wi < MAXW && ai < atom_cap) {
+              WEnd w;
+              const int sword = nr.stend;
+              const int transp = p.is_transp[sword];
+              w.j = k; w.atom = ai; w.last_word = transp ? tk.cword : sword;
+              w.base = tk.score;                                   // no wordend_a in multipath (beam.c:2307)
+              w.transp2 = (transp && tk.cword >= 0 && p.is_transp[tk.cword]) ? 1 : 0;
+              w.nintra = 0;
+              wend[wi] = w;
+              if (w.base > JB200_LOG_ZERO)
+                atomicMax(&s_webest, ((unsigned long long)fkey(w.base) << 32) | (unsigned)(~(unsigned)wi));
+            } else s_overflow = 1;
+          }
+        }
+        carry_a += tot_a; carry_w += tot_w;
+      }
+      if (tid == 0) { s_natoms = min(carry_a, atom_cap); s_E = min(carry_w, MAXW); }
+      nbits_b = carry_w * p.n_isoarc + p.n_sharc;
+      if (carry_w > MAXW || nbits_b > p.maxbits) { if (tid == 0) s_overflow = 1; nbits_b = 0; }
+    }
+    if (final) { n_left = ncre_a; __syncthreads(); break; }
+    nwords = (nbits_b + 31) >> 5;
+    for (int w = tid; w < nwords; w += BEAM_THREADS) bits[w] = 0u;
+    __syncthreads();
+    PROF_MARK(1);
+    const int E = (nbits_b > 0) ? s_E : 0;
+
+    // ---- B2: cross-word transitions through the isolated roots (beam.c:2336-2500), one candidate per
+    //          (word end, root successor), pre-reduced per successor over the word ends in visiting order
+    for (int ia = tid; ia < p.n_isoarc; ia += BEAM_THREADS) {
+      const int col = __ldg(p.iso_id + __ldg(p.isoarc_iso + ia));
+      const float pa = __ldg(p.isoarc_a + ia);
+      float best = JB200_LOG_ZERO, bestl = 0.0f; int beste = -1, firste = -1;
+      for (int e = 0; e < E; e++) {
+        const WEnd w = wend[e];
+        const float tmpprob = __ldg(p.iw + (size_t)w.last_word * p.n_iso + col);
+        const float lsc = tmpprob * p.lm_weight + p.lm_penalty;
+        float tmpsum = w.base;
+        tmpsum += lsc;
+        if (w.transp2) tmpsum += p.lm_penalty_trans;
+        const float v = tmpsum + pa;
+        if (v > JB200_LOG_ZERO) {
+          if (firste < 0) firste = e;
+          if (beste < 0 || best < v) { best = v; beste = e; bestl = lsc; }
+        }
+      }
+      IsoCand ic; ic.score = best; ic.e = beste; ic.lscore = bestl; ic.first_e = firste;
+      iso[ia] = ic;
+      if (firste >= 0) {
+        const unsigned sf = (unsigned)(wend[firste].j + 1) * SEQ_LOCAL + (unsigned)ia;
+        const unsigned sw = (unsigned)(wend[beste].j + 1) * SEQ_LOCAL + (unsigned)ia;
+        cand_atomics(firstseq, bestkey, __ldg(p.isoarc_node + ia), best, sf, sw);
+      }
+    }
+    // ---- B3: best word end -> successors of the shared (1-gram factored) roots (beam.c:2549-2616)
+    const unsigned long long webest = s_webest;
+    const bool have_we = (webest != 0ull) && (nbits_b > 0);
+    WEnd wbest; wbest.base = 0.0f; wbest.atom = -1; wbest.last_word = -1; wbest.transp2 = 0; wbest.j = 0; wbest.nintra = 0;
+    auto shared_value = [&](int sa, float &lsc, float &v) -> bool {
+      lsc = __ldg(p.shared_f + __ldg(p.sharc_shared + sa)) * p.lm_weight + p.lm_penalty;
+      float tmpsum = wbest.base;
+      tmpsum += lsc;
+      if (wbest.transp2) tmpsum += p.lm_penalty_trans;
+      if (tmpsum < thr) return false;
+      v = tmpsum + __ldg(p.sharc_a + sa);
+      return v > JB200_LOG_ZERO;
+    };
+    if (have_we) {
+      wbest = wend[(unsigned)(~(unsigned)(webest & 0xffffffffu))];
+      for (int sa = tid; sa < p.n_sharc; sa += BEAM_THREADS) {
+        float lsc, v;
+        if (!shared_value(sa, lsc, v)) continue;
+        const unsigned seq = (unsigned)(ns_a + 1) * SEQ_LOCAL + (unsigned)sa;
+        cand_atomics(firstseq, bestkey, __ldg(p.sharc_node + sa), v, seq, seq);
+      }
+    }
+    __syncthreads();
+    PROF_MARK(2);
+
+    // ---- B4: creators of half B (arrival order: word end major, then the factoring pass)
+    for (int ia = tid; ia < p.n_isoarc; ia += BEAM_THREADS) {
+      const IsoCand ic = iso[ia];
+      if (ic.first_e < 0) continue;
+      const unsigned sf = (unsigned)(wend[ic.first_e].j + 1) * SEQ_LOCAL + (unsigned)ia;
+      if ((unsigned)__ldcg(firstseq + __ldg(p.isoarc_node + ia)) == sf) {
+        const int pos = ic.first_e * p.n_isoarc + ia;
+        atomicOr(bits + (pos >> 5), 1u << (pos & 31));
+      }
+    }
+    if (have_we) {
+      for (int sa = tid; sa < p.n_sharc; sa += BEAM_THREADS) {
+        const unsigned seq = (unsigned)(ns_a + 1) * SEQ_LOCAL + (unsigned)sa;
+        if ((unsigned)__ldcg(firstseq + __ldg(p.sharc_node + sa)) == seq) {
+          const int pos = E * p.n_isoarc + sa;
+          atomicOr(bits + (pos >> 5), 1u << (pos & 31));
+        }
+      }
+    }
+    __syncthreads();
+    PROF_MARK(3);
+    int ncre;
+    {
+      int carry = 0;
+      for (int w0 = 0; w0 < nwords; w0 += BEAM_THREADS) {
+        const int w = w0 + tid;
+        const int cnt = (w < nwords) ? __popc(__ldcg(bits + w)) : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt, s_warp, &tot);
+        if (w < nwords) wpre[w] = carry + ex;
+        carry += tot;
+      }
+      ncre = ncre_a + carry;
+    }
+    if (ncre > MAXT) { if (tid == 0) s_overflow = 1; ncre = ncre_a; nbits_b = 0; }
+    __syncthreads();
+    PROF_MARK(4);
+
+    // ---- B5: new tokens get the winner's content; tokens of half A that lost to a cross-word arrival
+    //          are overwritten in place (propagate_token, beam.c:1901-1972)
+    auto winner_content = [&](unsigned seqw, Tok &nt) {
+      const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
+      if (j == ns_a + 1) {
+        float lsc, v;
+        shared_value(local, lsc, v);
+        nt.score = v; nt.lscore = lsc; nt.tre = wbest.atom; nt.cword = wbest.last_word; nt.tre_wid = araw[wbest.atom].wid;
+      } else {
+        const IsoCand ic = iso[local];
+        const WEnd w = wend[ic.e];
+        nt.score = ic.score; nt.lscore = ic.lscore; nt.tre = w.atom; nt.cword = w.last_word; nt.tre_wid = araw[w.atom].wid;
+      }
+    };
+    auto settle = [&](int node, unsigned seq_first, unsigned seq_win, int pos) {
+      const int fs = __ldcg(firstseq + node);
+      const unsigned seqw = ~(unsigned)(__ldcg(bestkey + node) & 0xffffffffu);
+      if (fs < 0) {
+        if (seqw != seq_win) return;
+        Tok nt; nt.node = node;
+        winner_content(seqw, nt);
+        tn[fs + TOK_EXISTS] = nt;
+      } else if ((unsigned)fs == seq_first) {
+        const unsigned wbits = __ldcg(bits + (pos >> 5));
+        const int r = ncre_a + wpre[pos >> 5] + __popc(wbits & ((1u << (pos & 31)) - 1u));
+        Tok nt; nt.node = node;
+        winner_content(seqw, nt);
+        tn[r] = nt;
+      }
+    };
+    if (nbits_b > 0) {
+      for (int ia = tid; ia < p.n_isoarc; ia += BEAM_THREADS) {
+        const IsoCand ic = iso[ia];
+        if (ic.first_e < 0) continue;
+        settle(__ldg(p.isoarc_node + ia), (unsigned)(wend[ic.first_e].j + 1) * SEQ_LOCAL + (unsigned)ia,
+               (unsigned)(wend[ic.e].j + 1) * SEQ_LOCAL + (unsigned)ia, ic.first_e * p.n_isoarc + ia);
+      }
+      if (have_we)
+        for (int sa = tid; sa < p.n_sharc; sa += BEAM_THREADS) {
+          float lsc, v;
+          if (!shared_value(sa, lsc, v)) continue;
+          const unsigned seq = (unsigned)(ns_a + 1) * SEQ_LOCAL + (unsigned)sa;
+          settle(__ldg(p.sharc_node + sa), seq, seq, E * p.n_isoarc + sa);
+        }
+    }
+    __syncthreads();
+
+    // ---- B6: output probabilities of the emitting tokens (beam.c:2930-2941); then the index array select #2
+    //          starts from: select #1's arrangement with fresh scores, followed by the tokens of half B
+    for (int r = tid; r < ncre; r += BEAM_THREADS) {
+      const Tok tk = tn[r];
+      const int out = p.nodes[tk.node].out;
+      float sc = tk.score;
+      if (((unsigned)out >> 28) != 0xFu) {
+        sc += outprob_style(p, row, out, tk.tre_wid);
+        tn[r].score = sc;
+        atomicMax(&s_pmaxkey, fkey(sc));
+      }
+      atomicMax(&s_hmaxkey, fkey(sc));
+      if (r >= ncre_a) heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(sc);
+    }
+    __syncthreads();
+    for (int h = 1 + tid; h <= ncre_a; h += BEAM_THREADS) {
+      const unsigned id = (unsigned)(heap[h] >> 32);
+      heap[h] = ((unsigned long long)id << 32) | __float_as_uint(tn[id].score);
+    }
+    __syncthreads();
+    PROF_MARK(5);
+
+    // ---- B7: heap select #2 (only its survivors' order is observable: loser cut allowed)
+    int ns_new;
+    {
+      const int need = p.beam, rest = ncre - need;
+      if (need >= ncre) {
+        ns_new = ncre;
+        // tindex order = select #1's arrangement, then the new tokens
+        for (int k = tid; k < ns_new; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
+      } else if (need < rest) {
+        ns_new = need;
+        constexpr int NB = 1024;
+        const int nb = min(NB, 2 * (p.beam + 2));
+        for (int i = tid; i < nb; i += BEAM_THREADS) hist[i] = 0;
+        __syncthreads();
+        const unsigned maxkey = s_hmaxkey;
+        const int e = (int)((((maxkey & 0x80000000u) ? (maxkey & 0x7fffffffu) : ~maxkey) >> 23) & 0xffu) - 127;
+        const int sh = max(0, min(24, 22 - e));
+        for (int r = tid; r < ncre; r += BEAM_THREADS) {
+          const unsigned key = fkey(hval(heap[r + 1]));
+          const unsigned bin = min((unsigned)(nb - 1), (maxkey - key) >> sh);
+          atomicAdd(&hist[bin], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+          int cum = 0, found = -1;
+          for (int b0 = 0; b0 < nb && found < 0; b0 += 32) {
+            const int v = (b0 + tid < nb) ? hist[b0 + tid] : 0;
+            int x = v;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
+            const unsigned hit = __ballot_sync(0xffffffffu, cum + x >= need);
+            if (hit) found = b0 + __ffs(hit) - 1;
+            cum += __shfl_sync(0xffffffffu, x, 31);
+          }
+          if (tid == 0) {
+            unsigned lk = 0u;
+            if (found >= 0 && found < nb - 1) {
+              const unsigned long long drop = (unsigned long long)(found + 1) << sh;
+              lk = (drop < maxkey) ? maxkey - (unsigned)drop : 0u;
+            }
+            s_losekey = lk;
+          }
+        }
+        __syncthreads();
+        const unsigned lk = s_losekey;
+        const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
+        heap_build<true>(heap, ncre); PROF_MARK(7);
+        heap_extract_lean<true>(heap, ncre, need, lose_below);
+        for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[ncre - need + 1 + k] >> 32);
+      } else {
+        ns_new = need;
+        heap_build<false>(heap, ncre); PROF_MARK(7);
+        heap_extract_lean<false>(heap, ncre, rest, -INFINITY);
+        for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
+      }
+    }
+    PROF_MARK(6);
+    if (tid == 0) {
+      counts[2 * t] = ncre; counts[2 * t + 1] = ns_new;
+      s_ns = ns_new; s_cur = nxt;
+      if (p.prune_width >= 0.0f) {
+        const unsigned k = s_pmaxkey;
+        const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+        s_thr = __uint_as_float(b) - p.prune_width;
+      } else s_thr = JB200_LOG_ZERO;
+    }
+    tnum_prev = ncre;
+    __syncthreads();
+    if (ncre == 0) { groups = t; break; }      // beam.c:3012-3015
   }
+
+  {
+    if (tid == 0 && T > 0) group0[groups] = s_natoms;
+    // leave the node slots clean for the next utterance that uses this work area
+    // (only the unfinished final frame leaves any: every other frame's slots are reset by the next P0)
+    const Tok *tlast = tok0 + (size_t)(s_cur ^ 1) * MAXT;
+    for (int i = tid; i < n_left; i += BEAM_THREADS) {
+      const int node = tlast[i].node;
+      __stcg(firstseq + node, 0x7fffffff);
+      __stcg(bestkey + node, 0ull);
+    }
+    __syncthreads();
+  }
+  finalize_utt(p, u, tid, T, araw, newidx, group0, res, words, s_natoms, s_overflow, s_found, s_outbase, s_prof, s_tprev);
 }
 
 // ---- set-up kernels ------------------------------------------------------------------------------
@@ -1040,7 +1583,6 @@ extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
 
 extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int max_utts, int max_frames, jb200_decoder **out) {
   if (!t || !am || !out || max_utts < 1 || max_frames < 1) { set_error("jb200_decoder_create: bad argument"); return JB200_ERR_ARG; }
-  if (t->multipath) { set_error("multipath HMMs are not supported by the GPU beam yet"); return JB200_ERR_UNSUPPORTED; }
   if (t->n_nodes >= (1 << 28)) { set_error("lexicon tree too large"); return JB200_ERR_UNSUPPORTED; }
   if (t->beam_width < 1 || t->beam_width > 8000) { set_error("beam width %d outside 1..8000", t->beam_width); return JB200_ERR_UNSUPPORTED; }
   jb200_decoder *d = new jb200_decoder();
@@ -1066,8 +1608,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     r.arc_off = t->arc_off[i]; r.arc_n = t->arc_off[i + 1] - t->arc_off[i];
     r.stend = t->stend[i]; r.scid = t->scid[i];
     const int style = t->outstyle[i];
-    if (style > 3) { set_error("non-emitting node in a non-multipath tree"); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
-    r.out = (int)(((unsigned)style << 28) | (unsigned)(t->out_ref[i] & 0x0fffffff));
+    if (style > 3 && !(style == 255 && t->multipath)) { set_error("non-emitting node in a non-multipath tree"); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
+    r.out = (style == 255) ? (int)0xF0000000u : (int)(((unsigned)style << 28) | (unsigned)(t->out_ref[i] & 0x0fffffff));
     r.pad = 0;
   }
   TRY(dev_upload(d, nodes.data(), nodes.size(), &P.nodes));
@@ -1090,6 +1632,33 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     TRY(dev_upload(d, sf.data(), (size_t)t->n_shared, &P.shared_f));
   }
   P.n_shared = t->n_shared;
+  P.multipath = t->multipath ? 1 : 0;
+  {
+    // multipath: expand the roots into their successors (self, next, arcs: the order propagation visits them,
+    // beam.c:2467-2500); the word-begin node of the head silence is never entered (beam.c:2336-2342)
+    std::vector<int> ia_node, ia_iso, sa_node, sa_sh; std::vector<float> ia_a, sa_a;
+    if (t->multipath) {
+      auto expand = [&](int root, int idx, std::vector<int> &vn, std::vector<int> &vi, std::vector<float> &va) {
+        if (t->self_a[root] != JB200_LOG_ZERO) { vn.push_back(root); vi.push_back(idx); va.push_back(t->self_a[root]); }
+        if (t->next_a[root] != JB200_LOG_ZERO) { vn.push_back(root + 1); vi.push_back(idx); va.push_back(t->next_a[root]); }
+        for (int k = t->arc_off[root]; k < t->arc_off[root + 1]; k++) { vn.push_back(t->arc_to[k]); vi.push_back(idx); va.push_back(t->arc_a[k]); }
+      };
+      const int head_begin = t->wordbegin[t->head_silwid];
+      for (int i = 0; i < t->n_iso; i++) if (t->iso_node[i] != head_begin) expand(t->iso_node[i], i, ia_node, ia_iso, ia_a);
+      for (int i = 0; i < t->n_shared; i++) expand(t->shared_node[i], i, sa_node, sa_sh, sa_a);
+    }
+    P.n_isoarc = (int)ia_node.size(); P.n_sharc = (int)sa_node.size();
+    TRY(dev_upload(d, ia_node.data(), ia_node.size(), &P.isoarc_node));
+    TRY(dev_upload(d, ia_iso.data(), ia_iso.size(), &P.isoarc_iso));
+    TRY(dev_upload(d, ia_a.data(), ia_a.size(), &P.isoarc_a));
+    TRY(dev_upload(d, sa_node.data(), sa_node.size(), &P.sharc_node));
+    TRY(dev_upload(d, sa_sh.data(), sa_sh.size(), &P.sharc_shared));
+    TRY(dev_upload(d, sa_a.data(), sa_a.size(), &P.sharc_a));
+    if (t->n_iso + 1024 >= (int)SEQ_LOCAL || P.n_isoarc >= (int)SEQ_LOCAL || P.n_sharc >= (int)SEQ_LOCAL || t->n_shared >= (int)SEQ_LOCAL) {
+      set_error("too many tree roots (%d isolated, %d shared) for the arrival-order numbering", t->n_iso, t->n_shared);
+      jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED;
+    }
+  }
   TRY(dev_upload(d, t->wordend_a, (size_t)t->n_words, &P.wordend_a));
   TRY(dev_upload(d, t->is_transparent, (size_t)t->n_words, &P.is_transp));
   TRY(dev_upload(d, t->wton, (size_t)t->n_words, &P.wton));
@@ -1136,9 +1705,10 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRY(dev_alloc(d, (size_t)max_utts * n, &P.firstseq));
   TRY(dev_alloc(d, (size_t)max_utts * n, &P.bestkey));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.cand));
-  TRY(dev_alloc(d, (size_t)max_utts * std::max(t->n_iso, 1), &P.iso));
+  const int n_isoent = std::max(std::max(t->n_iso, P.n_isoarc), 1);
+  TRY(dev_alloc(d, (size_t)max_utts * n_isoent, &P.iso));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxw, &P.wend));
-  P.maxbits = (P.maxc + std::min(P.maxw, 256) * std::max(t->n_iso, 1) + t->n_shared + 63) & ~31;
+  P.maxbits = (P.maxc + std::min(P.maxw, 256) * n_isoent + std::max(t->n_shared, P.n_sharc) + 63) & ~31;
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.bitmask));
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.wordpre));
   TRY(dev_alloc(d, (size_t)max_utts * (t->beam_width + 1), &P.outv));
@@ -1173,10 +1743,11 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
   d->smem_bytes = (size_t)(maxt + 4) * 8 + (size_t)(t->beam_width + 2) * 4 * 2;
-  TRYC(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
+  const void *kern = P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
+  TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
   {
     int per_sm = 0, sms = 0;
-    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, beam_kernel, BEAM_THREADS, d->smem_bytes));
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BEAM_THREADS, d->smem_bytes));
     TRYC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
     d->resident = per_sm * sms;
   }
@@ -1215,7 +1786,8 @@ static int launch_beam(jb200_decoder *d, int n_utts) {
   P.rows = d->d_rows; P.row_stride = d->row_stride; P.frame_off = d->d_frame_off;
   P.atom_off = d->d_atom_off; P.atoms_out = d->d_atoms_out; P.atom_counter = d->d_atom_counter;
   P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words; P.prof = d->d_prof;
-  beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
+  if (P.multipath) beam_kernel_mp<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
+  else beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   JB_LAUNCH_CHECK();
   return JB200_OK;
 }

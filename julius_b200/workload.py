@@ -29,6 +29,7 @@ WORKLOADS = {
     "mono100": ("mono100", []),                       # BASELINE configs[0]
     "tri20k": ("tri20k", []),                         # configs[1]: 3k states x 16 mix, 20k words, beam 800 (auto)
     "tri20k_gbeam": ("tri20k", ["-gprune", "beam"]),  # configs[2]: same with -gprune beam
+    "tri20k_mp": ("tri20k", ["-multipath"]),          # configs[1] with the multipath tree (non-emitting word begin/end nodes)
     "dnn20k": ("tri20k", ["-dnnconf", "@DNN@"]),      # configs[3]: DNN-HMM 528 -> 7x2048 -> 3000, 20k words
 }
 # DNN shapes (BASELINE configs[3]: ENVR-v5.4 shape 7x2048 sigmoid, 48x11 input)

@@ -52,8 +52,19 @@ def test_batch_order_and_repeat_are_deterministic():
             _check(r, u)
 
 
-def test_ragged_lengths_and_single_frame():
-    g = Golden("tiny")
+def test_multipath_work_areas_are_clean_after_each_batch():
+    """the multipath kernel leaves node slots set in its unfinished last frame and must reset them"""
+    g = Golden("small_mp")
+    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
+    for feats, utts in ((g.feats, g.utts), (g.feats[::-1], g.utts[::-1]), (g.feats, g.utts)):
+        for r, u in zip(dec.decode(feats), utts):
+            _check(r, u)
+
+
+@pytest.mark.parametrize("case", ["tiny", "small_mp"])
+def test_ragged_lengths_and_single_frame(case):
+    g = Golden(case)
     am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
     dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=2048)
     from oracle import ffi
@@ -67,8 +78,9 @@ def test_ragged_lengths_and_single_frame():
         assert r["status"] == o["status"] and r["words"] == o["words"]
 
 
-def test_frame_counts_match_oracle_trace():
-    g = Golden("small_b100")
+@pytest.mark.parametrize("case", ["small_b100", "small_mp"])
+def test_frame_counts_match_oracle_trace(case):
+    g = Golden(case)
     am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
     dec = capi.Decoder(g.ds, am, max_utts=4, max_frames=4096)
     from oracle import ffi

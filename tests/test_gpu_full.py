@@ -105,10 +105,10 @@ def test_full_size_heap_self_check(monkeypatch, oracle_lib):
     assert ok, why
 
 
-@pytest.mark.parametrize("name,frames", [("mono100", 400), ("tri20k_gbeam", 250)])
+@pytest.mark.parametrize("name,frames", [("mono100", 400), ("tri20k_gbeam", 250), ("tri20k_mp", 250)])
 def test_other_baseline_configs_end_to_end_vs_oracle(name, frames, oracle_lib):
     """BASELINE.json configs[0] (monophone 16-mix, 100 words) and configs[2] (-gprune beam, which is the
-    safe top-N algorithm for state-tied models): GPU end to end == CPU restatement, atom for atom."""
+    safe top-N algorithm for state-tied models), and configs[1] on the multipath tree (-multipath): GPU end to end == CPU restatement, atom for atom."""
     if not workload.ready(name):
         pytest.skip(f"workloads/{name} not prepared")
     blob = refdump.load_blob(workload.path(name, "model.jb2m"))

@@ -46,7 +46,7 @@ def test_attached_gpu_scores_drive_the_stock_beam(case, tmp_path):
         assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
 
 
-@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_safe"])
+@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_safe", "small_mp"])
 def test_stock_host_with_gpu_beam_linked_in(case, tmp_path):
     from oracle import ffi
     g, d, files = _prepare(case, tmp_path)
