@@ -14,8 +14,8 @@
  *                                                    pass-1 best exactly where find_1pass_result does
  *                                                    (beam.c:497-512)
  *   fsbeam_free(d)                       beam.c:3180
- * Restrictions (checked, fail loudly): N-gram LM, non-multipath AM, no short-pause segmentation,
- * buffered input.  The models are flattened on first use with the same code as the plugin.
+ * Restrictions (checked, fail loudly): N-gram LM, no short-pause segmentation, buffered input
+ * (normal and multipath trees both run on the device).  The models are flattened on first use with the same code as the plugin.
  */
 #include <julius/juliuslib.h>
 #include "jb200_model.h"
@@ -46,8 +46,8 @@ static Shim *shim_for(RecogProcess *r, int frames) {
   if (!g_api_loaded) { if (jb200_api_load(&g_api, (void *)&shim_for) != 0) return NULL; g_api_loaded = 1; }
   if (s == NULL) {
     if (g_nshim >= 8) { jlog("ERROR: jb200: too many recognition instances\n"); return NULL; }
-    if (r->lmtype != LM_PROB || r->am->hmminfo->multipath || r->config->successive.enabled) {
-      jlog("ERROR: jb200: the GPU beam supports N-gram, non-multipath, non-segmented decoding only\n");
+    if (r->lmtype != LM_PROB || r->config->successive.enabled) {
+      jlog("ERROR: jb200: the GPU beam supports N-gram, non-segmented decoding only\n");
       return NULL;
     }
     s = &g_shim[g_nshim];

@@ -44,6 +44,7 @@ class SynthConfig:
     max_wlen: int = 5
     monophone: bool = False    # context-independent AM (config[0])
     one_phone_words: int = 0   # number of 1-phone words (exercise AS_LRSET)
+    sp_model: bool = False     # add a 1-state tee model "sp" (skip transition) for -iwsp; forces multipath
 
     @staticmethod
     def preset(name: str) -> "SynthConfig":
@@ -53,6 +54,9 @@ class SynthConfig:
             return SynthConfig(name="small", seed=2, n_phones=12, n_states=240, n_mix=8,
                                phys_per_phone=24, vocab=400, n_bigrams=4000,
                                min_wlen=2, max_wlen=6, one_phone_words=3)
+        if name == "small_sp":   # "small" plus a short-pause tee model (-iwsp, multipath by necessity)
+            c = SynthConfig.preset("small")
+            return dataclasses.replace(c, name="small_sp", sp_model=True)
         if name == "mono100":    # BASELINE config[0]: monophone 16-mix, 100 words
             return SynthConfig(name="mono100", seed=3, n_phones=40, n_states=120, n_mix=16,
                                phys_per_phone=1, vocab=100, n_bigrams=1500,
@@ -180,10 +184,17 @@ class SynthModel:
                 for k in range(3):
                     f.write(f'<STATE> {k + 2}\n~s "st{st[k]}"\n')
                 f.write(f'~t "{self.trans_names[ti]}"\n<ENDHMM>\n')
+            if cfg.sp_model:
+                # short pause: one emitting state (the middle state of a silence model) that can be skipped
+                st = self.phys[self.phys_of[(0, 0)]][1][1]
+                f.write(f'~h "sp"\n<BEGINHMM>\n<NUMSTATES> 3\n<STATE> 2\n~s "st{st}"\n<TRANSP> 3\n')
+                f.write(" 0.0 0.7 0.3\n 0.0 0.6 0.4\n 0.0 0.0 0.0\n<ENDHMM>\n")
 
     def write_hmmlist(self, path: str) -> None:
         P = self.cfg.n_phones
         with open(path, "w") as f:
+            if self.cfg.sp_model:
+                f.write("sp sp\n")
             if self.cfg.monophone:
                 for c in range(P):
                     f.write(f"{self.phones[c]} {self.phys[self.phys_of[(c, 0)]][0]}\n")

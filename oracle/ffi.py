@@ -107,8 +107,9 @@ def have_ref() -> bool:
 
 def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "out.jrf", export: str | None = None,
             tokens: bool = False, am_args: list | None = None, quiet: bool = True, timeout: int = 3600,
-            binary: str | None = None, env_extra: dict | None = None):
-    """Run the compiled reference on HTK parameter files; returns (dump path, stdout)."""
+            binary: str | None = None, env_extra: dict | None = None, two_pass: bool = False):
+    """Run the compiled reference on HTK parameter files; returns (dump path, stdout).
+    two_pass: also run the stack-decoding pass 2 and print its sentences (JREF_RESULT lines)."""
     env = dict(os.environ)
     if quiet:
         env["JREF_QUIET"] = "1"
@@ -116,11 +117,13 @@ def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "ou
         env["JREF_TOKENS"] = "1"
     if export:
         env["JB200_EXPORT"] = export
+    if two_pass:
+        env["JREF_RESULT"] = "1"
     if env_extra:
         env.update(env_extra)
     args = [binary or JREF, "-dump", os.path.join(workdir, dump), "-plugindir", PLUGDIR]
     args += am_args if am_args is not None else ["-h", "hmmdefs", "-hlist", "hmmlist"]
-    args += ["-v", "dict", "-nlr", "lm.arpa", "-input", "mfcfile", "-1pass", "-outprobout", "/dev/null"]
+    args += ["-v", "dict", "-nlr", "lm.arpa", "-input", "mfcfile"] + ([] if two_pass else ["-1pass"]) + ["-outprobout", "/dev/null"]
     args += list(extra_args)
     p = subprocess.run(args, input="\n".join(filelist) + "\n", text=True, cwd=workdir, env=env,
                        capture_output=True, timeout=timeout)

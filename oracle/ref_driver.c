@@ -136,6 +136,23 @@ static void on_pass1_end(Recog *recog, void *dummy) {
   fflush(g_out);
 }
 
+/* full two-pass runs (no -1pass): the final sentence hypotheses, for end-to-end host checks */
+static void on_result(Recog *recog, void *dummy) {
+  RecogProcess *r = recog->process_list;
+  int n, i;
+  fprintf(stdout, "JREF_RESULT utt=%d status=%d", g_utt - 1, r->result.status);
+  if (r->result.status >= 0) {
+    for (n = 0; n < r->result.sentnum; n++) {
+      Sentence *st = &(r->result.sent[n]);
+      union { float f; unsigned u; } sc;
+      sc.f = st->score;
+      fprintf(stdout, " sent%d=%08x:", n, sc.u);
+      for (i = 0; i < st->word_num; i++) fprintf(stdout, "%s%d", i ? "," : "", (int)st->word[i]);
+    }
+  }
+  fprintf(stdout, "\n");
+}
+
 int main(int argc, char *argv[]) {
   Jconf *jconf;
   Recog *recog;
@@ -162,6 +179,7 @@ int main(int argc, char *argv[]) {
   callback_add(recog, CALLBACK_EVENT_PASS1_BEGIN, on_pass1_begin, NULL);
   callback_add(recog, CALLBACK_EVENT_PASS1_FRAME, on_pass1_frame, NULL);
   callback_add(recog, CALLBACK_EVENT_PASS1_END, on_pass1_end, NULL);
+  if (getenv("JREF_RESULT")) callback_add(recog, CALLBACK_RESULT, on_result, NULL);
   if (j_adin_init(recog) == FALSE) return 1;
 
   if (jconf->input.speech_input == SP_MFCFILE || jconf->input.speech_input == SP_OUTPROBFILE) {

@@ -31,10 +31,15 @@ CASES = {
     "small_safe": ("small", 1, 150, 0, ["-gprune", "safe", "-tmix", "2", "-b", "60", "-iwcd1", "max"]),
     # multipath tree (non-emitting word-begin/word-end nodes), beam.c:2752-2828
     "small_mp": ("small", 2, 200, 1, ["-multipath", "-b", "120"]),
+    # inter-word short pause (tee model => multipath by necessity), BASELINE configs[4] flavour
+    "small_iwsp": ("small_sp", 2, 200, 1, ["-iwsp", "-iwcd1", "max", "-b", "150"]),
 }
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {
     "small_dnn": ("small", dict(in_dim=120, feature_len=40, context_len=3, hidden=128, layers=3), 2, 150, ["-b", "150"]),
+    # configs[4] flavour: DNN-HMM on a multipath tree with -iwsp and a wide beam
+    "small_dnn_iwsp": ("small_sp", dict(in_dim=120, feature_len=40, context_len=3, hidden=128, layers=3), 2, 150,
+                       ["-iwsp", "-iwcd1", "max", "-b", "600"]),
 }
 
 

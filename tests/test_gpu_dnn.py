@@ -3,13 +3,14 @@ import numpy as np
 import pytest
 
 from julius_b200 import capi
-from util import Golden, atoms_equal, rel_err
+from util import DNN_CASES, Golden, atoms_equal, rel_err
 
 pytestmark = pytest.mark.gpu
 
 
-def test_dnn_scores_within_1e4_relative_of_reference():
-    g = Golden("small_dnn")
+@pytest.mark.parametrize("case", DNN_CASES)
+def test_dnn_scores_within_1e4_relative_of_reference(case):
+    g = Golden(case)
     dnn = capi.DnnScorer(g.ds)
     for u, x in zip(g.utts, g.feats):
         out = dnn.score(x)
@@ -30,11 +31,12 @@ def test_dnn_ragged_batches():
         assert np.abs(part - full[:T]).max() <= 1e-5
 
 
-def test_decode_with_dnn_scores_matches_reference_words():
+@pytest.mark.parametrize("case", DNN_CASES)
+def test_decode_with_dnn_scores_matches_reference_words(case):
     """DNN scoring -> GPU beam.  Scores differ from the reference by <=1e-4 so the trellis is compared
     through the beam run on the reference's own score matrix (bit-exact) and, end to end, by the
-    pass-1 best word sequence."""
-    g = Golden("small_dnn")
+    pass-1 best word sequence.  small_dnn_iwsp = BASELINE configs[4] flavour (multipath tree, -iwsp, wide beam)."""
+    g = Golden(case)
     am = capi.GmmScorer(g.ds, gmm_desc=g.ds.cd_only_gmm())
     dec = capi.Decoder(g.ds, am, max_utts=4, max_frames=2048)
     res = dec.decode_scores([u.outprob for u in g.utts])

@@ -32,7 +32,7 @@ def _prepare(case, tmp_path):
     return g, d, files
 
 
-@pytest.mark.parametrize("case", ["tiny", "small_b100"])
+@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_iwsp"])
 def test_attached_gpu_scores_drive_the_stock_beam(case, tmp_path):
     from oracle import ffi
     g, d, files = _prepare(case, tmp_path)
@@ -46,7 +46,7 @@ def test_attached_gpu_scores_drive_the_stock_beam(case, tmp_path):
         assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
 
 
-@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_safe", "small_mp"])
+@pytest.mark.parametrize("case", ["tiny", "small_b100", "small_safe", "small_mp", "small_iwsp"])
 def test_stock_host_with_gpu_beam_linked_in(case, tmp_path):
     from oracle import ffi
     g, d, files = _prepare(case, tmp_path)
@@ -58,3 +58,26 @@ def test_stock_host_with_gpu_beam_linked_in(case, tmp_path):
         assert ok, why
         assert u.status == ref.status
         assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+
+
+def _results(out):
+    return [ln for ln in out.splitlines() if ln.startswith("JREF_RESULT")]
+
+
+@pytest.mark.parametrize("case", ["small_b100", "small_iwsp"])
+def test_full_two_pass_recognition_is_unchanged_by_either_boundary(case, tmp_path):
+    """the stock host runs BOTH passes; pass 2 (stack decoding on the word trellis,
+    re-reading the state scores through outprob_state) must produce the same sentences and scores when
+    (a) the GPU fills the score cache, (b) the GPU beam builds the trellis, (c) both."""
+    from oracle import ffi
+    g, d, files = _prepare(case, tmp_path)
+    _, stock = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], two_pass=True, dump="stock.jrf")
+    want = _results(stock)
+    assert len(want) == len(files) and all("sent0=" in w for w in want[:2])
+    _, a = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], two_pass=True, dump="a.jrf", env_extra={"JB200_ATTACH": "1"})
+    assert _results(a) == want
+    _, b = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], two_pass=True, dump="b.jrf", binary=ffi.JREF_GPU)
+    assert _results(b) == want
+    _, c = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], two_pass=True, dump="c.jrf", binary=ffi.JREF_GPU,
+                       env_extra={"JB200_ATTACH": "1"})
+    assert _results(c) == want

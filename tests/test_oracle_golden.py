@@ -3,7 +3,7 @@ in tests/golden bit for bit -- this is what pins the oracle (prompt section 3)."
 import numpy as np
 import pytest
 
-from util import CASES, Golden, atoms_equal
+from util import CASES, DNN_CASES, Golden, atoms_equal
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -46,10 +46,11 @@ def test_cdset_scores_consistent_with_states(oracle_lib):
         assert abs(cd[5, c] - v.astype(np.float64).mean()) < 1e-3
 
 
-def test_dnn_restatement_bit_exact_and_beam_on_dnn_scores(oracle_lib):
+@pytest.mark.parametrize("case", DNN_CASES)
+def test_dnn_restatement_bit_exact_and_beam_on_dnn_scores(case, oracle_lib):
     """DNN-HMM: the restatement of dnn_calc_outprob (x86 FMA GEMV order, logistic table, addlog
     softmax, prior) equals the compiled reference bit for bit; the beam restatement runs on it."""
-    g = Golden("small_dnn")
+    g = Golden(case)
     for u, x in zip(g.utts, g.feats):
         sc = oracle_lib.dnn_score(g.ds, x)
         assert np.array_equal(sc.view(np.uint32), u.outprob.view(np.uint32))

@@ -7,7 +7,8 @@ from julius_b200 import desc, refdump
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["tiny", "small_b100", "small_safe", "small_mp"]
+CASES = ["tiny", "small_b100", "small_safe", "small_mp", "small_iwsp"]
+DNN_CASES = ["small_dnn", "small_dnn_iwsp"]
 
 
 class Golden:
