@@ -310,6 +310,7 @@ def product_main(a):
     phase = dec.phase_cycles(min(B, 64)).mean(0)
     n_ok = sum(1 for r in res if r["status"] == 0 and r["overflow"] == 0)
     counts = dec.frame_counts(0, T)
+    hs = dec.heap_stats()
 
     # max over ranks
     vals = torch.tensor([dev_ms, (t1 - t0) * 1000.0, (t3 - t2) * 1000.0], dtype=torch.float64, device=device)
@@ -366,7 +367,8 @@ def product_main(a):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                     "ms_per_step": e2e_ms_max / a.steps},
             "gpu_launches": int(launches),
-            "decoded_ok": f"{n_ok}/{len(res)}", "heap_misspeculations": dec.misspeculations(), "clocks": clocks,
+            "decoded_ok": f"{n_ok}/{len(res)}", "heap_misspeculations": dec.misspeculations(),
+            "heap_levels_per_extraction": round(hs["levels"] / max(hs["extractions"], 1), 3), "clocks": clocks,
         }
         if world == 1 and not a.no_cpu_baseline:
             try:

@@ -149,6 +149,8 @@ int jb200_decoder_sync_timing(jb200_decoder *d);
 int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d);
 /* how often (frames, since create) the pipelined heap replay had to fall back to the sequential one */
 int64_t jb200_decoder_misspeculations(jb200_decoder *d);
+/* beam-cut replay counters since create: out[0] fall-backs, out[1] heap levels walked, out[2] extractions */
+int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]);
 /* how many utterances (thread blocks) are co-resident on the device for this decoder */
 int jb200_decoder_resident_utts(const jb200_decoder *d);
 /* SM-cycle totals per kernel phase of the first n_utts utterances of the last batch: cycles [n_utts][8]

@@ -69,6 +69,7 @@ def lib():
             L.jb200_decoder_resident_utts.argtypes = [vp]
             L.jb200_decoder_misspeculations.argtypes = [vp]
             L.jb200_decoder_misspeculations.restype = C.c_int64
+            L.jb200_decoder_heap_stats.argtypes = [vp, C.POINTER(C.c_int64)]
             L.jb200_decoder_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
         _lib = L
     return _lib
@@ -247,6 +248,12 @@ class Decoder:
 
     def misspeculations(self) -> int:
         return int(lib().jb200_decoder_misspeculations(self._h))
+
+    def heap_stats(self) -> dict:
+        """beam-cut replay counters since create"""
+        v = (C.c_int64 * 3)()
+        _check(lib().jb200_decoder_heap_stats(self._h, v), "jb200_decoder_heap_stats")
+        return {"fallbacks": int(v[0]), "levels": int(v[1]), "extractions": int(v[2])}
 
     def resident_utts(self) -> int:
         return int(lib().jb200_decoder_resident_utts(self._h))

@@ -349,6 +349,89 @@ __device__ void heap_extract_lean(unsigned long long *A, const int n, const int 
   __syncthreads();
 }
 
+// Fast single-thread extraction replay.  Same comparisons as heap_extract_lean, arranged so that the
+// loop-carried dependence of one tree level is  LDS.128 -> compare -> select next address -> LDS.128 :
+//   * a freed tail slot is overwritten with a sentinel (-inf for the max-heap, +inf for the min-heap) and
+//     so is everything between n+1 and the last child slot (heap_pad_sentinels), which makes both bounds
+//     tests of the reference loop ("child <= n", "child < n") fall out of the value comparisons: a
+//     missing right child never wins, a missing pair stops the sift;
+//   * the children of BOTH possible next parents have known addresses before the comparison resolves, so
+//     the next pair is requested right after the compare, ahead of the stop test (a harmless read when
+//     the sift ends; addresses are clamped to a sentinel pair at the end of the array).  ptxas sinks a
+//     load below the branch when nothing on the exit path reads it, and ld.volatile costs ~50 cycles per
+//     level (tools/ubench/heapx.cu: 97 vs 54 cycles/level), hence the `sink` value that the exit path
+//     folds into the statistics word;
+//   * the extracted roots go to `outv` (k-th extracted at outv[k]) instead of the tail slots.
+// ~45 instead of ~100 cycles per level.  Ends with a barrier.
+template <bool MAXHEAP>
+__device__ __forceinline__ void heap_pad_sentinels(unsigned long long *A, const int n, const int maxt) {
+  const unsigned long long sent = MAXHEAP ? 0xff800000ull : 0x7f800000ull;
+  const int hi = min(2 * n + 1, maxt + 1);
+  for (int i = n + 1 + (int)threadIdx.x; i <= hi; i += BEAM_THREADS) A[i] = sent;
+  if (threadIdx.x < 2) A[maxt + 2 + threadIdx.x] = sent;
+}
+
+template <bool MAXHEAP>
+__device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned a_left, unsigned a_right, bool &right) {
+  // "child < child+1" (beam.c:1359 / :1425) and the address of the chosen child's own children, one select
+  unsigned r, pr;
+  if (MAXHEAP) asm("{ .reg .pred p; setp.lt.f32 p, %4, %5; selp.u32 %0, %2, %3, p; selp.u32 %1, 1, 0, p; }"
+                   : "=r"(r), "=r"(pr) : "r"(a_right), "r"(a_left), "f"(__uint_as_float(x0)), "f"(__uint_as_float(y0)));
+  else asm("{ .reg .pred p; setp.gt.f32 p, %4, %5; selp.u32 %0, %2, %3, p; selp.u32 %1, 1, 0, p; }"
+           : "=r"(r), "=r"(pr) : "r"(a_right), "r"(a_left), "f"(__uint_as_float(x0)), "f"(__uint_as_float(y0)));
+  right = (pr != 0u);
+  return r;
+}
+
+// one tree level: pair (X0,X1),(Y0,Y1) = children of the parent at `slot`; requests the next pair into N*
+#define JB_HEAP_LEVEL(X0, X1, Y0, Y1, N0, N1, N2, N3)                                                        \
+  {                                                                                                          \
+    const unsigned u = (cur << 1) - hb;                                                                      \
+    bool right;                                                                                              \
+    const unsigned ncur = heap_pick<MAXHEAP>(X0, Y0, min(u, capa), min(u + 16u, capa), right);               \
+    lds_pair(ncur, N0, N1, N2, N3);                      /* speculative: children of the chosen child */     \
+    sink = N0;                                           /* (read on the exit path too, see below) */        \
+    const unsigned c_lo = right ? Y0 : X0, c_hi = right ? Y1 : X1;                                           \
+    levels++;                                                                                                \
+    if (hstop<MAXHEAP>(sv, __uint_as_float(c_lo)) || (MAXHEAP && __uint_as_float(c_lo) < lose_below)) break; \
+    sts_one(slot, c_lo, c_hi);                                                                               \
+    slot = cur + (right ? 8u : 0u);                                                                          \
+    cur = ncur;                                                                                              \
+  }
+
+template <bool MAXHEAP>
+__device__ void heap_extract_fast(unsigned long long *A, const int n, const int extract, const float lose_below,
+                                  unsigned long long *outv, const int maxt, unsigned long long *stats) {
+  if (threadIdx.x == 0) {
+    unsigned levels = 0, sink = 0, sinkacc = 0;
+    const unsigned hb = smem_u32(A);
+    const unsigned sent = MAXHEAP ? 0xff800000u : 0x7f800000u;
+    const unsigned capa = hb + (((unsigned)(maxt >> 1) + 1u) << 4);    // pair (maxt+2, maxt+3): always sentinels
+    unsigned mslot = hb + ((unsigned)n << 3);
+    for (int x = 0; x < extract; x++) {
+      unsigned s_lo, s_hi, r_lo, r_hi, x0, x1, y0, y1, z0, z1, w0, w1;
+      lds_one(mslot, s_lo, s_hi);                       // s = A[m]
+      sts_one(mslot, sent, 0u);                         // slot m leaves the heap (before the root's children are read)
+      lds_one(hb + 8u, r_lo, r_hi);                     // root
+      lds_pair(hb + 16u, x0, x1, y0, y1);               // its children
+      mslot -= 8u;
+      outv[x] = ((unsigned long long)r_hi << 32) | r_lo;
+      const float sv = __uint_as_float(s_lo);
+      unsigned slot = hb + 8u, cur = hb + 16u;          // address of the parent slot / of its children pair
+      while (true) {
+        JB_HEAP_LEVEL(x0, x1, y0, y1, z0, z1, w0, w1)
+        JB_HEAP_LEVEL(z0, z1, w0, w1, x0, x1, y0, y1)
+      }
+      sts_one(slot, s_lo, s_hi);
+      sinkacc += sink;
+    }
+    atomicAdd(stats + 1, (unsigned long long)levels); atomicAdd(stats + 2, (unsigned long long)extract);
+    atomicAdd(stats + 3, (unsigned long long)sinkacc);
+  }
+  __syncthreads();
+}
+#undef JB_HEAP_LEVEL
+
 // Pipelined extraction replay, warp 0, lock-step.  Lane k of the warp owns the extractions x with
 // x mod NL == k; every extraction in flight advances exactly one tree level per "tick" and a new one
 // starts at least two ticks after the previous one, so extraction x always works two levels above x-1:
@@ -882,15 +965,19 @@ beam_kernel(const BeamParams p) {
             __syncthreads();
             const unsigned lk = s_losekey;
             const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
+            heap_pad_sentinels<true>(heap, ncre, MAXT);
             heap_build<true>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) {
+            if (p.heap_mode == 0) heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter);
+            else if (p.heap_mode == 2) {
               heap_extract_lean<true>(heap, ncre, extract, lose_below);
-              for (int k = tid; k < extract; k += BEAM_THREADS) outv[k] = heap[ncre - k];   // same convention as the pipelined replay
+              for (int k = tid; k < extract; k += BEAM_THREADS) outv[k] = heap[ncre - k];   // same convention as the other replays
               __syncthreads();
             } else heap_extract_pipelined<true>(heap, ncre, extract, outv, lose_below);
           } else {
+            heap_pad_sentinels<false>(heap, ncre, MAXT);
             heap_build<false>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) heap_extract_lean<false>(heap, ncre, extract, -INFINITY);
+            if (p.heap_mode == 0) heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter);
+            else if (p.heap_mode == 2) heap_extract_lean<false>(heap, ncre, extract, -INFINITY);
             else heap_extract_pipelined<false>(heap, ncre, extract, outv, -INFINITY);
           }
           ok = true;
@@ -986,10 +1073,17 @@ beam_kernel(const BeamParams p) {
 // Half B reuses the per-node slots: a token made in half A keeps the slot with firstseq = id - 2^30 (< 0:
 // "exists") and bestkey = (score, seq 0), so later arrivals only replace its content when strictly better.
 template <bool MAXHEAP>
-__device__ __forceinline__ int select_exact(unsigned long long *heap, int n, int need, int *ordn) {
-  // sort_token_no_order (beam.c:1492-1520), replayed in place; returns the first survivor's slot
+__device__ __forceinline__ int select_exact(unsigned long long *heap, int n, int need, int *ordn, unsigned long long *outv, int maxt,
+                                            unsigned long long *stats) {
+  // sort_token_no_order (beam.c:1492-1520) replayed in full; the extracted roots are put back into the
+  // tail slots where the in-place algorithm leaves them (k-th extracted at slot n-k).  Returns the first
+  // survivor's slot.
+  const int extract = MAXHEAP ? need : n - need;
+  heap_pad_sentinels<MAXHEAP>(heap, n, maxt);
   heap_build<MAXHEAP>(heap, n);
-  heap_extract_lean<MAXHEAP>(heap, n, MAXHEAP ? need : n - need, -INFINITY);
+  heap_extract_fast<MAXHEAP>(heap, n, extract, -INFINITY, outv, maxt, stats);
+  for (int k = threadIdx.x; k < extract; k += BEAM_THREADS) heap[n - k] = outv[k];
+  __syncthreads();
   const int start = MAXHEAP ? n - need : 0;
   for (int k = threadIdx.x; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[start + k + 1] >> 32);
   return start;
@@ -1196,8 +1290,8 @@ beam_kernel_mp(const BeamParams p) {
         for (int k = tid; k < ns_a; k += BEAM_THREADS) ordn[k] = k;
       } else {
         ns_a = need;
-        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn);
-        else select_exact<false>(heap, ncre_a, need, ordn);
+        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter);
+        else select_exact<false>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter);
       }
     }
     __syncthreads();
@@ -1462,13 +1556,15 @@ beam_kernel_mp(const BeamParams p) {
         __syncthreads();
         const unsigned lk = s_losekey;
         const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
+        heap_pad_sentinels<true>(heap, ncre, MAXT);
         heap_build<true>(heap, ncre); PROF_MARK(7);
-        heap_extract_lean<true>(heap, ncre, need, lose_below);
-        for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[ncre - need + 1 + k] >> 32);
+        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter);
+        for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
       } else {
         ns_new = need;
+        heap_pad_sentinels<false>(heap, ncre, MAXT);
         heap_build<false>(heap, ncre); PROF_MARK(7);
-        heap_extract_lean<false>(heap, ncre, rest, -INFINITY);
+        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
       }
     }
@@ -1712,11 +1808,11 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.bitmask));
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.wordpre));
   TRY(dev_alloc(d, (size_t)max_utts * (t->beam_width + 1), &P.outv));
-  TRY(dev_alloc(d, 1, &P.misspec_counter));
-  TRYC(cudaMemset(P.misspec_counter, 0, sizeof(unsigned long long)));
+  TRY(dev_alloc(d, 4, &P.misspec_counter));        // [0] mis-speculations, [1] sift levels, [2] extractions
+  TRYC(cudaMemset(P.misspec_counter, 0, 4 * sizeof(unsigned long long)));
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
   P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
-  P.heap_mode = getenv("JB200_HEAP_MODE") ? atoi(getenv("JB200_HEAP_MODE")) : 0;   // 0 lean sequential (+loser cut), 1 lock-step pipelined
+  P.heap_mode = getenv("JB200_HEAP_MODE") ? atoi(getenv("JB200_HEAP_MODE")) : 0;   // 0 fast sequential (sentinels, speculative loads), 1 lock-step pipelined, 2 lean sequential
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   {
     size_t tot = (size_t)max_utts * n;
@@ -1859,6 +1955,15 @@ extern "C" int64_t jb200_decoder_misspeculations(jb200_decoder *d) {
   cudaSetDevice(d->device);
   if (cudaMemcpy(&v, d->P.misspec_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v;
+}
+
+extern "C" int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]) {
+  if (!d || !out) { set_error("bad argument"); return JB200_ERR_ARG; }
+  unsigned long long v[3] = {0, 0, 0};
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaMemcpy(v, d->P.misspec_counter, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 3; i++) out[i] = (int64_t)v[i];
+  return JB200_OK;
 }
 
 extern "C" int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d) { return d ? d->last_d2h : 0; }

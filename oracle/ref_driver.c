@@ -136,6 +136,18 @@ static void on_pass1_end(Recog *recog, void *dummy) {
   fflush(g_out);
 }
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+/* a crash inside the host libraries is reported with a symbolic backtrace (no debugger on the test boxes) */
+static void on_crash(int sig) {
+  void *bt[48];
+  int n = backtrace(bt, 48);
+  fprintf(stderr, "jref: signal %d, backtrace:\n", sig);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
+
 /* full two-pass runs (no -1pass): the final sentence hypotheses, for end-to-end host checks */
 static void on_result(Recog *recog, void *dummy) {
   RecogProcess *r = recog->process_list;
@@ -167,6 +179,7 @@ int main(int argc, char *argv[]) {
     args[nargs++] = argv[i];
   }
   if (dump == NULL) { fprintf(stderr, "usage: jref -dump out.jrf [julius options]\n"); return 2; }
+  signal(SIGSEGV, on_crash); signal(SIGBUS, on_crash); signal(SIGABRT, on_crash);
   if (getenv("JREF_TOKENS")) g_tokens = atoi(getenv("JREF_TOKENS"));
   if (getenv("JREF_QUIET")) jlog_set_output(NULL);
   g_out = fopen(dump, "wb");

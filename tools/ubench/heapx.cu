@@ -1,0 +1,154 @@
+// heapx.cu -- micro-benchmark of the beam-cut extraction replay on a realistic heap (n=2400 random scores,
+// 800 extractions, loser cut at the 800th largest).  Variants isolate what a level / an extraction costs.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o heapx heapx.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define MAXT 3328
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lds_pair_spec(unsigned a, unsigned &x0, unsigned &x1, unsigned &y0, unsigned &y1) {
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_pair(unsigned a, unsigned &x0, unsigned &x1, unsigned &y0, unsigned &y1) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_one(unsigned a, unsigned &x0, unsigned &x1) {
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_one(unsigned a, unsigned x0, unsigned x1) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(x0), "r"(x1) : "memory");
+}
+__device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned a_left, unsigned a_right, bool &right) {
+  unsigned r, pr;
+  asm("{ .reg .pred p; setp.lt.f32 p, %4, %5; selp.u32 %0, %2, %3, p; selp.u32 %1, 1, 0, p; }"
+      : "=r"(r), "=r"(pr) : "r"(a_right), "r"(a_left), "f"(__uint_as_float(x0)), "f"(__uint_as_float(y0)));
+  right = (pr != 0u);
+  return r;
+}
+
+// V: 0 = as in beam.cu; 1 = outv in shared memory; 2 = no loser-cut test; 3 = non-volatile (sinkable) load;
+//    4 = one level per loop trip (no ping-pong unroll); 5 = plain load whose result is also consumed on the
+//    exit path (ptxas must issue it ahead of the stop test); 6 = 5 + both grandchild pairs requested one level
+//    ahead (two-level speculation)
+#define LEVEL(X0, X1, Y0, Y1, N0, N1, N2, N3)                                                        \
+  {                                                                                                  \
+    const unsigned u = (cur << 1) - hb;                                                              \
+    bool right;                                                                                      \
+    const unsigned ncur = heap_pick(X0, Y0, min(u, capa), min(u + 16u, capa), right);                \
+    if (V == 3 || V >= 5) lds_pair(ncur, N0, N1, N2, N3); else lds_pair_spec(ncur, N0, N1, N2, N3);  \
+    if (V >= 5) sink = N0;                                                                           \
+    const unsigned c_lo = right ? Y0 : X0, c_hi = right ? Y1 : X1;                                   \
+    levels++;                                                                                        \
+    if (sv >= __uint_as_float(c_lo) || (V != 2 && __uint_as_float(c_lo) < lose_below)) break;        \
+    sts_one(slot, c_lo, c_hi);                                                                       \
+    slot = cur + (right ? 8u : 0u);                                                                  \
+    cur = ncur;                                                                                      \
+  }
+
+template <int V>
+__global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int n, int extract, float lose_below,
+                                            unsigned long long *outg, long long *res) {
+  __shared__ __align__(16) unsigned long long A[MAXT + 4];
+  __shared__ unsigned long long outs[1024];
+  for (int i = threadIdx.x; i < MAXT + 4; i += blockDim.x) A[i] = (i >= 1 && i <= n) ? init[i] : 0xff800000ull;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long *outv = (V == 1) ? outs : outg + (size_t)blockIdx.x * 1024;
+    unsigned levels = 0, sink = 0, sinkacc = 0;
+    const unsigned hb = smem_u32(A);
+    const unsigned capa = hb + (((unsigned)(MAXT >> 1) + 1u) << 4);
+    unsigned mslot = hb + ((unsigned)n << 3);
+    long long t0 = clock64();
+    for (int x = 0; x < extract; x++) {
+      unsigned s_lo, s_hi, r_lo, r_hi, x0, x1, y0, y1, z0, z1, w0, w1;
+      lds_one(mslot, s_lo, s_hi);
+      sts_one(mslot, 0xff800000u, 0u);
+      lds_one(hb + 8u, r_lo, r_hi);
+      lds_pair(hb + 16u, x0, x1, y0, y1);
+      mslot -= 8u;
+      outv[x] = ((unsigned long long)r_hi << 32) | r_lo;
+      const float sv = __uint_as_float(s_lo);
+      unsigned slot = hb + 8u, cur = hb + 16u;
+      if (V == 4) {
+        while (true) {
+          LEVEL(x0, x1, y0, y1, z0, z1, w0, w1)
+          x0 = z0; x1 = z1; y0 = w0; y1 = w1;
+        }
+      } else {
+        while (true) {
+          LEVEL(x0, x1, y0, y1, z0, z1, w0, w1)
+          LEVEL(z0, z1, w0, w1, x0, x1, y0, y1)
+        }
+      }
+      sts_one(slot, s_lo, s_hi);
+      sinkacc += sink;
+    }
+    long long t1 = clock64();
+    if (V >= 5) outv[1000] = sinkacc;
+    res[blockIdx.x * 2] = t1 - t0;
+    res[blockIdx.x * 2 + 1] = levels;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && V == 1) for (int i = threadIdx.x; i < extract; i += blockDim.x) outg[i] = outs[i];
+}
+
+int main() {
+  const int n = 2400, extract = 800;
+  std::vector<unsigned long long> h(MAXT + 4, 0);
+  std::vector<float> sc(n + 1);
+  srand(7);
+  for (int i = 1; i <= n; i++) sc[i] = -30000.0f - (float)(rand() % 200000) / 512.0f;     // coarse grid => ties
+  // host max-heap build (same sift-down as the reference) so that the device starts from a valid heap
+  auto val = [&](int i) { return sc[i]; };
+  std::vector<int> idx(n + 1); for (int i = 1; i <= n; i++) idx[i] = i;
+  for (int root = n / 2; root >= 1; root--) {
+    int s = idx[root]; int parent = root, child;
+    while ((child = parent * 2) <= n) {
+      if (child < n && val(idx[child]) < val(idx[child + 1])) child++;
+      if (val(s) >= val(idx[child])) break;
+      idx[parent] = idx[child]; parent = child;
+    }
+    idx[parent] = s;
+  }
+  for (int i = 1; i <= n; i++) { unsigned b; float f = sc[idx[i]]; memcpy(&b, &f, 4); h[i] = ((unsigned long long)idx[i] << 32) | b; }
+  std::vector<float> sorted(sc.begin() + 1, sc.end()); std::sort(sorted.begin(), sorted.end(), std::greater<float>());
+  const float lose_below = sorted[extract - 1] - 0.5f;
+  // host reference extraction order
+  std::vector<int> ref;
+  { std::vector<int> a(idx); int m = n;
+    for (int x = 0; x < extract; x++) { int s = a[m]; ref.push_back(a[1]); a[m] = a[1]; m--; int parent = 1, child;
+      while ((child = parent * 2) <= m) { if (child < m && val(a[child]) < val(a[child + 1])) child++; if (val(s) >= val(a[child])) break; a[parent] = a[child]; parent = child; }
+      a[parent] = s; } }
+  unsigned long long *d, *o; long long *r, hr[2 * 592];
+  cudaMalloc(&d, sizeof(unsigned long long) * (MAXT + 4)); cudaMemcpy(d, h.data(), sizeof(unsigned long long) * (MAXT + 4), cudaMemcpyHostToDevice);
+  cudaMalloc(&o, sizeof(unsigned long long) * 1024 * 592); cudaMalloc(&r, sizeof(hr));
+  std::vector<unsigned long long> ho(1024);
+  for (int blocks : {1, 148, 592}) {
+    for (int v = 0; v < 6; v++) {
+      for (int rep = 0; rep < 2; rep++) {
+        switch (v) {
+          case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 1: k<1><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 2: k<2><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 3: k<3><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 4: k<4><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 5: k<5><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+        }
+        cudaDeviceSynchronize();
+      }
+      cudaMemcpy(hr, r, sizeof(long long) * 2 * blocks, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ho.data(), o, sizeof(unsigned long long) * 1024, cudaMemcpyDeviceToHost);
+      int bad = 0; for (int x = 0; x < extract; x++) if ((int)(ho[x] >> 32) != ref[x]) bad++;
+      double s = 0, l = 0; for (int b = 0; b < blocks; b++) { s += (double)hr[2 * b]; l += (double)hr[2 * b + 1]; }
+      printf("blocks %3d variant %d: %.0f cycles/extraction, %.2f levels/extraction, %.1f cycles/level, order mismatches %d\n",
+             blocks, v, s / blocks / extract, l / blocks / extract, s / l, bad);
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
