@@ -91,6 +91,9 @@ boolean get_back_trellis_init(HTK_Param *param, RecogProcess *r) {
   bt_prepare(r->backtrellis);
   r->pass1.bos.wid = WORD_INVALID;
   r->pass1.bos.begintime = r->pass1.bos.endtime = -1;
+  /* host-side state that init_nodescore resets per utterance and pass 2 relies on (beam.c:1595):
+   * the per-node triphone caches of outprob_style (bt_discount_pescore and the stack decoder read them) */
+  outprob_style_cache_init(r->wchmm);
   r->config->output.progout_interval_frame = (int)((float)r->config->output.progout_interval / ((float)param->header.wshift / 10000.0));
   s = shim_for(r, T);
   if (s == NULL) return FALSE;
