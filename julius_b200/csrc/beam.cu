@@ -58,6 +58,19 @@ struct __align__(16) Cand { float score; int node; float lscore; int src; };    
 struct __align__(16) IsoCand { float score; int e; float lscore; int first_e; };                                 // 16 B
 struct __align__(8) WEnd { int j; int atom; int last_word; float base; int transp2; int nintra; };              // 24 B
 
+// per-node arrival slot: who reached the node first (creator) and who reached it best (content); one aligned
+// 16-byte record so that the two atomics, the reset and the later reads of a node touch a single sector
+struct __align__(16) NodeSlot { unsigned long long bestkey; int firstseq; int pad; };
+struct SlotView {
+  NodeSlot *s;
+  __device__ __forceinline__ int *fs(int node) const { return &s[node].firstseq; }
+  __device__ __forceinline__ unsigned long long *bk(int node) const { return &s[node].bestkey; }
+  __device__ __forceinline__ void set(int node, int firstseq, unsigned long long bestkey) const {
+    __stcg(reinterpret_cast<uint4 *>(s + node), make_uint4((unsigned)bestkey, (unsigned)(bestkey >> 32), (unsigned)firstseq, 0u));
+  }
+  __device__ __forceinline__ void reset(int node) const { set(node, 0x7fffffff, 0ull); }
+};
+
 struct BeamParams {
   // tree
   const NodeRec *nodes; const int *arc_to; const float *arc_a;
@@ -79,7 +92,7 @@ struct BeamParams {
   // batch
   const float *rows; int row_stride; const int *frame_off;
   // per-utterance work areas (index = blockIdx.x)
-  Tok *tok; int *order; int *firstseq; unsigned long long *bestkey; Cand *cand; IsoCand *iso; WEnd *wend;
+  Tok *tok; int *order; NodeSlot *slots; Cand *cand; IsoCand *iso; WEnd *wend;
   jb200_atom *atoms_raw; int *newidx; int *group0; int *counts;
   const long long *atom_off;
   // compact outputs
@@ -88,7 +101,8 @@ struct BeamParams {
   long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
   unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
   unsigned long long *outv;          // per-utterance extracted heap roots [beam+1]
-  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, heap_mode;
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, heap_mode, prof_fine;
+  unsigned long long *lmc; int lmc_bits;      // memo of max_successor_prob, 2^lmc_bits entries (0 = off)
   int maxt, maxc, maxw, maxbits;
 };
 
@@ -127,12 +141,27 @@ __device__ float bigram_prob(const BeamParams &p, int w1, int w2) {
   return prob - p.lm_unk_num_log;
 }
 
-// max_successor_prob, factoring_sub.c:942-1012 (1-gram factoring build)
+// max_successor_prob, factoring_sub.c:942-1012 (1-gram factoring build).  The reference keeps a per-node
+// one-entry cache of the bigram look-up (factoring_sub.c:984-1006); here a direct-mapped table shared by
+// all utterances memoises the pure function (last word, successor-word slot) -> value, because the binary
+// search is ~10 dependent global loads and the same pairs recur every frame while a token waits on the
+// node in front of a single-word branch.  One 64-bit word per entry: key in the high half, value bits in
+// the low half, written and read atomically as a unit.
 __device__ __forceinline__ float max_successor_prob(const BeamParams &p, int lastword, int scid) {
   if (lastword < 0) return 0.0f;
   if (scid < 0) return __ldg(p.fscore - scid);
+  unsigned long long *slot = nullptr;
+  unsigned key = 0u;
+  if (p.lmc_bits > 0) {
+    key = ((unsigned)lastword << 16) | (unsigned)scid;
+    slot = p.lmc + ((key * 2654435761u) >> (32 - p.lmc_bits));
+    const unsigned long long e = __ldcg(slot);
+    if ((unsigned)(e >> 32) == key) return __uint_as_float((unsigned)e);
+  }
   int w = __ldg(p.scword + scid);
-  return bigram_prob(p, __ldg(p.wton + lastword), __ldg(p.wton + w)) + __ldg(p.cprob + w);
+  const float v = bigram_prob(p, __ldg(p.wton + lastword), __ldg(p.wton + w)) + __ldg(p.cprob + w);
+  if (slot) __stcg(slot, ((unsigned long long)key << 32) | __float_as_uint(v));
+  return v;
 }
 
 // outprob_cd, outprob.c:286-400, evaluated on demand from the frame's state-score row
@@ -148,6 +177,25 @@ __device__ float cdset_score(const BeamParams &p, const float *__restrict__ row,
     return mx;
   }
   const int maxn = p.iwcd_nbest;
+  if (maxn <= 3) {
+    // the kept list is the sorted multiset of the maxn largest valid scores, and the result adds it up from the
+    // largest down (outprob.c:313-318): three registers instead of an indexed array in local memory
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY; int n = 0;
+    for (int i = 0; i < n_in; i++) {
+      const float v = __ldg(row + __ldg(p.cd_states + b0 + i));
+      if (v <= JB200_LOG_ZERO) continue;
+      n++;
+      if (v > m0) { m2 = m1; m1 = m0; m0 = v; }
+      else if (v > m1) { m2 = m1; m1 = v; }
+      else if (v > m2) m2 = v;
+    }
+    n = min(n, maxn);
+    float prob = 0.0f;
+    if (n > 0) prob += m0;
+    if (n > 1) prob += m1;
+    if (n > 2) prob += m2;
+    return prob / (float)n;
+  }
   float mp[CD_NMAX + 1]; int n = 0;
   for (int i = 0; i < n_in; i++) {
     float prob = __ldg(row + __ldg(p.cd_states + b0 + i));
@@ -205,11 +253,11 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_sums, int *total
   return r;
 }
 
-__device__ __forceinline__ void cand_atomics(int *firstseq, unsigned long long *bestkey,
+__device__ __forceinline__ void cand_atomics(const SlotView &slots,
                                              int node, float score, unsigned seq_first, unsigned seq_win) {
-  atomicMin(firstseq + node, (int)seq_first);
+  atomicMin(slots.fs(node), (int)seq_first);
   unsigned long long key = ((unsigned long long)fkey(score) << 32) | (unsigned)(~seq_win);
-  atomicMax(bestkey + node, key);
+  atomicMax(slots.bk(node), key);
 }
 
 // heap entries: high 32 bits = token id, low 32 bits = fp32 score bits.  Heap index h (1-based) lives
@@ -363,6 +411,18 @@ __device__ void heap_extract_lean(unsigned long long *A, const int n, const int 
 //     folds into the statistics word;
 //   * the extracted roots go to `outv` (k-th extracted at outv[k]) instead of the tail slots.
 // ~45 instead of ~100 cycles per level.  Ends with a barrier.
+// work for the otherwise idle warps during a single-thread extraction replay: reset the per-node slots of the
+// tokens created in this frame (clear_tokens, beam.c:1122, moved ahead of the next frame)
+struct SlotClear {
+  const Tok *tok; int n; SlotView slots;
+  __device__ __forceinline__ void run(int first, int stride) const {
+    for (int i = first; i < n; i += stride) {
+      const int node = tok[i].node;
+      slots.reset(node);
+    }
+  }
+};
+
 template <bool MAXHEAP>
 __device__ __forceinline__ void heap_pad_sentinels(unsigned long long *A, const int n, const int maxt) {
   const unsigned long long sent = MAXHEAP ? 0xff800000ull : 0x7f800000ull;
@@ -401,7 +461,9 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
 
 template <bool MAXHEAP>
 __device__ void heap_extract_fast(unsigned long long *A, const int n, const int extract, const float lose_below,
-                                  unsigned long long *outv, const int maxt, unsigned long long *stats) {
+                                  unsigned long long *outv, const int maxt, unsigned long long *stats,
+                                  const SlotClear *idle_work = nullptr) {
+  if (threadIdx.x >= 32 && idle_work) idle_work->run((int)threadIdx.x - 32, BEAM_THREADS - 32);
   if (threadIdx.x == 0) {
     unsigned levels = 0, sink = 0, sinkacc = 0;
     const unsigned hb = smem_u32(A);
@@ -605,8 +667,7 @@ beam_kernel(const BeamParams p) {
 
   Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
   int *ord0 = p.order + (size_t)u * 2 * MAXT;
-  int *firstseq = p.firstseq + (size_t)u * p.n_nodes;
-  unsigned long long *bestkey = p.bestkey + (size_t)u * p.n_nodes;
+  const SlotView slots{p.slots + (size_t)u * p.n_nodes};
   Cand *cand = p.cand + (size_t)u * MAXC;
   IsoCand *iso = p.iso + (size_t)u * max(p.n_iso, 1);
   WEnd *wend = p.wend + (size_t)u * MAXW;
@@ -644,6 +705,7 @@ beam_kernel(const BeamParams p) {
 
   int tnum_prev = (T > 0) ? 1 : 0;      // tokens created in the previous frame (clear phase)
   int groups = T;                       // number of end-frame groups kept by finalize (framelen)
+  bool slots_clean = false;             // the previous frame's node slots were already reset under its beam cut
 
   // ================= frames 1..T-1: get_back_trellis_proceed (beam.c:2663-3019) =================
   for (int t = 1; t < T; t++) {
@@ -654,12 +716,15 @@ beam_kernel(const BeamParams p) {
     const float thr = s_thr;
     const float *row = p.rows + (size_t)(f_begin + t) * p.row_stride;
 
-    // ---- P0: clear_tokens (beam.c:1122): reset the node slots used by frame t-1
-    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
-      const int node = tl[i].node;
-      __stcg(firstseq + node, 0x7fffffff);
-      __stcg(bestkey + node, 0ull);
+    // ---- P0: clear_tokens (beam.c:1122): reset the node slots used by frame t-1 (normally done already by
+    //          the idle warps while thread 0 replayed that frame's heap select, see P6)
+    if (!slots_clean) {
+      for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+        const int node = tl[i].node;
+        slots.reset(node);
+      }
     }
+    slots_clean = false;
     if (tid == 0) { s_ncre = 0; s_webest = 0ull; s_pmaxkey = 0u; group0[t - 1] = s_natoms; }
     __syncthreads();
     PROF_MARK(0);
@@ -729,40 +794,40 @@ beam_kernel(const BeamParams p) {
     PROF_MARK(1);
     const int E = (nbits > 0) ? s_E : 0;
 
-    // ---- P2a: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177)
-    if (cand_total > 0) {
-      for (int j = tid; j < ns; j += BEAM_THREADS) {
-        const int c0 = offs[j], nin = offs[j + 1] - c0;
-        if (nin == 0) continue;
-        const Tok tk = tl[ordl[j]];
-        const NodeRec nr = p.nodes[tk.node];
-        int k = 0;
-        for (int a = -2; a < nr.arc_n; a++) {
-          int next; float pa;
-          if (a == -2) { if (nr.self_a == JB200_LOG_ZERO) continue; next = tk.node; pa = nr.self_a; }
-          else if (a == -1) { if (nr.next_a == JB200_LOG_ZERO) continue; next = tk.node + 1; pa = nr.next_a; }
-          else { next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
-          float tmpsum = tk.score + pa;
-          float lsc = JB200_LOG_ZERO;
-          if (next != tk.node) {
-            const int scid = p.nodes[next].scid;
-            if (scid != 0) {
-              lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
-              tmpsum -= tk.lscore;
-              tmpsum += lsc;
-            }
-          }
-          if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
-          Cand c; c.score = tmpsum; c.node = next; c.lscore = lsc; c.src = j;
-          cand[c0 + k] = c;
-          if (tmpsum > JB200_LOG_ZERO) {
-            const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
-            cand_atomics(firstseq, bestkey, next, tmpsum, seq, seq);
-          }
-          k++;
+    // ---- P2a: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177), one thread per
+    //           candidate (survivors near the tree roots fan out 10-20 ways: per-survivor loops leave most
+    //           of the block idle); the owner of candidate c is found by bisection of the offsets
+    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
+      int lo = 0, hi = ns;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= c) lo = mid; else hi = mid; }
+      const int j = lo;
+      int k = c - offs[j];
+      const Tok tk = tl[ordl[j]];
+      const NodeRec nr = p.nodes[tk.node];
+      int next; float pa;
+      const int has_self = (nr.self_a != JB200_LOG_ZERO), has_next = (nr.next_a != JB200_LOG_ZERO);
+      if (has_self && k == 0) { next = tk.node; pa = nr.self_a; }
+      else if (has_next && k == has_self) { next = tk.node + 1; pa = nr.next_a; }
+      else { const int a = k - has_self - has_next; next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
+      float tmpsum = tk.score + pa;
+      float lsc = JB200_LOG_ZERO;
+      if (next != tk.node) {
+        const int scid = p.nodes[next].scid;
+        if (scid != 0) {
+          lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
+          tmpsum -= tk.lscore;
+          tmpsum += lsc;
         }
       }
+      if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
+      Cand cd; cd.score = tmpsum; cd.node = next; cd.lscore = lsc; cd.src = j;
+      cand[c] = cd;
+      if (tmpsum > JB200_LOG_ZERO) {
+        const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
+        cand_atomics(slots, next, tmpsum, seq, seq);
+      }
     }
+    if (p.prof_fine) { __syncthreads(); PROF_MARK(4); }
     // ---- P2b: cross-word transitions into isolated roots (beam_inter_word, beam.c:2271-2517),
     //           pre-reduced per root over this frame's word ends, visited in survivor order
     for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
@@ -786,7 +851,7 @@ beam_kernel(const BeamParams p) {
         const WEnd wf = wend[firste], wb = wend[beste];
         const unsigned sf = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
         const unsigned sw = (unsigned)wb.j * SEQ_LOCAL + (unsigned)(wb.nintra + i);
-        cand_atomics(firstseq, bestkey, __ldg(p.iso_node + i), best, sf, sw);
+        cand_atomics(slots, __ldg(p.iso_node + i), best, sf, sw);
       }
     }
     // ---- P2c: best word end -> shared (1-gram factored) roots (beam_inter_word_factoring, :2549-2616)
@@ -803,7 +868,7 @@ beam_kernel(const BeamParams p) {
         if (tmpsum < thr) continue;
         if (tmpsum > JB200_LOG_ZERO) {
           const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
-          cand_atomics(firstseq, bestkey, __ldg(p.shared_node + i), tmpsum, seq, seq);
+          cand_atomics(slots, __ldg(p.shared_node + i), tmpsum, seq, seq);
         }
       }
     }
@@ -817,7 +882,7 @@ beam_kernel(const BeamParams p) {
       if (!(cd.score > JB200_LOG_ZERO)) continue;
       const int k = c - offs[cd.src];
       const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)k;
-      if ((unsigned)__ldcg(firstseq + cd.node) == seq) {
+      if ((unsigned)__ldcg(slots.fs(cd.node)) == seq) {
         const int pos = poff[cd.src] + k;
         atomicOr(bits + (pos >> 5), 1u << (pos & 31));
       }
@@ -827,7 +892,7 @@ beam_kernel(const BeamParams p) {
       if (ic.first_e < 0) continue;
       const WEnd wf = wend[ic.first_e];
       const unsigned seq = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
-      if ((unsigned)__ldcg(firstseq + __ldg(p.iso_node + i)) == seq) {
+      if ((unsigned)__ldcg(slots.fs(__ldg(p.iso_node + i))) == seq) {
         const int pos = poff[wf.j] + wf.nintra + i;
         atomicOr(bits + (pos >> 5), 1u << (pos & 31));
       }
@@ -835,7 +900,7 @@ beam_kernel(const BeamParams p) {
     if (have_we) {
       for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
         const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
-        if ((unsigned)__ldcg(firstseq + __ldg(p.shared_node + i)) == seq) {
+        if ((unsigned)__ldcg(slots.fs(__ldg(p.shared_node + i))) == seq) {
           const int pos = poff[ns] + i;
           atomicOr(bits + (pos >> 5), 1u << (pos & 31));
         }
@@ -867,7 +932,7 @@ beam_kernel(const BeamParams p) {
       const unsigned wbits = __ldcg(bits + (pos >> 5));
       if (!((wbits >> (pos & 31)) & 1u)) return;
       const int r = wpre[pos >> 5] + __popc(wbits & ((1u << (pos & 31)) - 1u));
-      const unsigned long long bk = __ldcg(bestkey + node);
+      const unsigned long long bk = __ldcg(slots.bk(node));
       const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
       const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
       Tok nt; nt.node = node;
@@ -925,6 +990,12 @@ beam_kernel(const BeamParams p) {
         const int extract = upward ? need : rest;
         ns_new = need;
         bool ok = false;
+        // the node slots of this frame are dead from here on: warps 1.. reset them for the next frame while
+        // thread 0 is busy with the extraction replay (SlotClear, run inside heap_extract_fast*)
+        const SlotClear sc{tn, ncre, slots};
+        const bool fastpath = !p.force_seq_heap && (p.heap_mode == 0);
+        if (!fastpath) sc.run((int)threadIdx.x, BEAM_THREADS);
+        slots_clean = true;
         if (!p.force_seq_heap) {
           if (upward) {
             // lower bound of the need-th largest score from a 1024-bin histogram of the order-preserving
@@ -967,7 +1038,7 @@ beam_kernel(const BeamParams p) {
             const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
             heap_pad_sentinels<true>(heap, ncre, MAXT);
             heap_build<true>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter);
+            if (p.heap_mode == 0) heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter, &sc);
             else if (p.heap_mode == 2) {
               heap_extract_lean<true>(heap, ncre, extract, lose_below);
               for (int k = tid; k < extract; k += BEAM_THREADS) outv[k] = heap[ncre - k];   // same convention as the other replays
@@ -976,7 +1047,7 @@ beam_kernel(const BeamParams p) {
           } else {
             heap_pad_sentinels<false>(heap, ncre, MAXT);
             heap_build<false>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter);
+            if (p.heap_mode == 0) heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
             else if (p.heap_mode == 2) heap_extract_lean<false>(heap, ncre, extract, -INFINITY);
             else heap_extract_pipelined<false>(heap, ncre, extract, outv, -INFINITY);
           }
@@ -1049,10 +1120,11 @@ beam_kernel(const BeamParams p) {
     }
     if (tid == 0) { s_natoms = min(carry_a, atom_cap); group0[groups] = s_natoms; }
     // leave the node slots clean for the next utterance that uses this work area
-    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
-      const int node = tl[i].node;
-      __stcg(firstseq + node, 0x7fffffff);
-      __stcg(bestkey + node, 0ull);
+    if (!slots_clean) {
+      for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+        const int node = tl[i].node;
+        slots.reset(node);
+      }
     }
     __syncthreads();
   }
@@ -1111,8 +1183,7 @@ beam_kernel_mp(const BeamParams p) {
 
   Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
   int *ord0 = p.order + (size_t)u * 2 * MAXT;
-  int *firstseq = p.firstseq + (size_t)u * p.n_nodes;
-  unsigned long long *bestkey = p.bestkey + (size_t)u * p.n_nodes;
+  const SlotView slots{p.slots + (size_t)u * p.n_nodes};
   Cand *cand = p.cand + (size_t)u * MAXC;
   IsoCand *iso = p.iso + (size_t)u * max(max(p.n_iso, p.n_isoarc), 1);
   WEnd *wend = p.wend + (size_t)u * MAXW;
@@ -1149,6 +1220,7 @@ beam_kernel_mp(const BeamParams p) {
   int tnum_prev = (T > 0) ? 1 : 0;
   int groups = T;
   int n_left = 0;             // tokens of the unfinished (final) frame whose node slots are still set
+  bool slots_clean = false;   // the previous frame's node slots were already reset under its second beam cut
 
   // frames 0..T-1 (pass1.c:239-245 calls proceed(0) right after init), then proceed(T, final) (beam.c:3066-3072)
   for (int t = 0; t <= T && T > 0; t++) {
@@ -1160,12 +1232,14 @@ beam_kernel_mp(const BeamParams p) {
     const float thr = s_thr;
     const float *row = p.rows + (size_t)(f_begin + (final ? 0 : t)) * p.row_stride;
 
-    // ---- P0: clear_tokens
-    for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
-      const int node = tl[i].node;
-      __stcg(firstseq + node, 0x7fffffff);
-      __stcg(bestkey + node, 0ull);
+    // ---- P0: clear_tokens (normally done already under the previous frame's select #2)
+    if (!slots_clean) {
+      for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
+        const int node = tl[i].node;
+        slots.reset(node);
+      }
     }
+    slots_clean = false;
     if (tid == 0) { s_webest = 0ull; s_pmaxkey = fkey(JB200_LOG_ZERO); s_hmaxkey = 0u; if (t > 0) group0[t - 1] = s_natoms; }
     __syncthreads();
     PROF_MARK(0);
@@ -1197,38 +1271,37 @@ beam_kernel_mp(const BeamParams p) {
     __syncthreads();
     PROF_MARK(1);
 
-    // ---- A2: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177)
-    if (cand_total > 0) {
-      for (int j = tid; j < ns; j += BEAM_THREADS) {
-        const int c0 = offs[j], nin = offs[j + 1] - c0;
-        if (nin == 0) continue;
-        const Tok tk = tl[ordl[j]];
-        const NodeRec nr = p.nodes[tk.node];
-        int k = 0;
-        for (int a = -2; a < nr.arc_n; a++) {
-          int next; float pa;
-          if (a == -2) { if (nr.self_a == JB200_LOG_ZERO) continue; next = tk.node; pa = nr.self_a; }
-          else if (a == -1) { if (nr.next_a == JB200_LOG_ZERO) continue; next = tk.node + 1; pa = nr.next_a; }
-          else { next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
-          float tmpsum = tk.score + pa;
-          float lsc = JB200_LOG_ZERO;
-          if (next != tk.node) {
-            const int scid = p.nodes[next].scid;
-            if (scid != 0) {
-              lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
-              tmpsum -= tk.lscore;
-              tmpsum += lsc;
-            }
-          }
-          if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
-          Cand c; c.score = tmpsum; c.node = next; c.lscore = lsc; c.src = j;
-          cand[c0 + k] = c;
-          if (tmpsum > JB200_LOG_ZERO) {
-            const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
-            cand_atomics(firstseq, bestkey, next, tmpsum, seq, seq);
-          }
-          k++;
+    // ---- A2: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177), one thread per
+    //           candidate (survivors near the tree roots fan out 10-20 ways: per-survivor loops leave most
+    //           of the block idle); the owner of candidate c is found by bisection of the offsets
+    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
+      int lo = 0, hi = ns;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= c) lo = mid; else hi = mid; }
+      const int j = lo;
+      int k = c - offs[j];
+      const Tok tk = tl[ordl[j]];
+      const NodeRec nr = p.nodes[tk.node];
+      int next; float pa;
+      const int has_self = (nr.self_a != JB200_LOG_ZERO), has_next = (nr.next_a != JB200_LOG_ZERO);
+      if (has_self && k == 0) { next = tk.node; pa = nr.self_a; }
+      else if (has_next && k == has_self) { next = tk.node + 1; pa = nr.next_a; }
+      else { const int a = k - has_self - has_next; next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
+      float tmpsum = tk.score + pa;
+      float lsc = JB200_LOG_ZERO;
+      if (next != tk.node) {
+        const int scid = p.nodes[next].scid;
+        if (scid != 0) {
+          lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
+          tmpsum -= tk.lscore;
+          tmpsum += lsc;
         }
+      }
+      if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
+      Cand cd; cd.score = tmpsum; cd.node = next; cd.lscore = lsc; cd.src = j;
+      cand[c] = cd;
+      if (tmpsum > JB200_LOG_ZERO) {
+        const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
+        cand_atomics(slots, next, tmpsum, seq, seq);
       }
     }
     __syncthreads();
@@ -1239,7 +1312,7 @@ beam_kernel_mp(const BeamParams p) {
       const Cand cd = cand[c];
       if (!(cd.score > JB200_LOG_ZERO)) continue;
       const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)(c - offs[cd.src]);
-      if ((unsigned)__ldcg(firstseq + cd.node) == seq) atomicOr(bits + (c >> 5), 1u << (c & 31));
+      if ((unsigned)__ldcg(slots.fs(cd.node)) == seq) atomicOr(bits + (c >> 5), 1u << (c & 31));
     }
     __syncthreads();
     PROF_MARK(3);
@@ -1266,7 +1339,7 @@ beam_kernel_mp(const BeamParams p) {
       if (!((wbits >> (c & 31)) & 1u)) continue;
       const int r = wpre[c >> 5] + __popc(wbits & ((1u << (c & 31)) - 1u));
       const int node = cand[c].node;
-      const unsigned long long bk = __ldcg(bestkey + node);
+      const unsigned long long bk = __ldcg(slots.bk(node));
       const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
       const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
       const Cand cd = cand[offs[j] + local];
@@ -1275,8 +1348,7 @@ beam_kernel_mp(const BeamParams p) {
       nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = src.tre; nt.cword = src.cword; nt.tre_wid = src.tre_wid;
       tn[r] = nt;
       heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
-      __stcg(firstseq + node, r - TOK_EXISTS);
-      __stcg(bestkey + node, ((unsigned long long)fkey(nt.score) << 32) | 0xffffffffull);
+      slots.set(node, r - TOK_EXISTS, ((unsigned long long)fkey(nt.score) << 32) | 0xffffffffull);
     }
     __syncthreads();
     PROF_MARK(5);
@@ -1376,7 +1448,7 @@ beam_kernel_mp(const BeamParams p) {
       if (firste >= 0) {
         const unsigned sf = (unsigned)(wend[firste].j + 1) * SEQ_LOCAL + (unsigned)ia;
         const unsigned sw = (unsigned)(wend[beste].j + 1) * SEQ_LOCAL + (unsigned)ia;
-        cand_atomics(firstseq, bestkey, __ldg(p.isoarc_node + ia), best, sf, sw);
+        cand_atomics(slots, __ldg(p.isoarc_node + ia), best, sf, sw);
       }
     }
     // ---- B3: best word end -> successors of the shared (1-gram factored) roots (beam.c:2549-2616)
@@ -1398,7 +1470,7 @@ beam_kernel_mp(const BeamParams p) {
         float lsc, v;
         if (!shared_value(sa, lsc, v)) continue;
         const unsigned seq = (unsigned)(ns_a + 1) * SEQ_LOCAL + (unsigned)sa;
-        cand_atomics(firstseq, bestkey, __ldg(p.sharc_node + sa), v, seq, seq);
+        cand_atomics(slots, __ldg(p.sharc_node + sa), v, seq, seq);
       }
     }
     __syncthreads();
@@ -1409,7 +1481,7 @@ beam_kernel_mp(const BeamParams p) {
       const IsoCand ic = iso[ia];
       if (ic.first_e < 0) continue;
       const unsigned sf = (unsigned)(wend[ic.first_e].j + 1) * SEQ_LOCAL + (unsigned)ia;
-      if ((unsigned)__ldcg(firstseq + __ldg(p.isoarc_node + ia)) == sf) {
+      if ((unsigned)__ldcg(slots.fs(__ldg(p.isoarc_node + ia))) == sf) {
         const int pos = ic.first_e * p.n_isoarc + ia;
         atomicOr(bits + (pos >> 5), 1u << (pos & 31));
       }
@@ -1417,7 +1489,7 @@ beam_kernel_mp(const BeamParams p) {
     if (have_we) {
       for (int sa = tid; sa < p.n_sharc; sa += BEAM_THREADS) {
         const unsigned seq = (unsigned)(ns_a + 1) * SEQ_LOCAL + (unsigned)sa;
-        if ((unsigned)__ldcg(firstseq + __ldg(p.sharc_node + sa)) == seq) {
+        if ((unsigned)__ldcg(slots.fs(__ldg(p.sharc_node + sa))) == seq) {
           const int pos = E * p.n_isoarc + sa;
           atomicOr(bits + (pos >> 5), 1u << (pos & 31));
         }
@@ -1457,8 +1529,8 @@ beam_kernel_mp(const BeamParams p) {
       }
     };
     auto settle = [&](int node, unsigned seq_first, unsigned seq_win, int pos) {
-      const int fs = __ldcg(firstseq + node);
-      const unsigned seqw = ~(unsigned)(__ldcg(bestkey + node) & 0xffffffffu);
+      const int fs = __ldcg(slots.fs(node));
+      const unsigned seqw = ~(unsigned)(__ldcg(slots.bk(node)) & 0xffffffffu);
       if (fs < 0) {
         if (seqw != seq_win) return;
         Tok nt; nt.node = node;
@@ -1558,13 +1630,17 @@ beam_kernel_mp(const BeamParams p) {
         const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
         heap_pad_sentinels<true>(heap, ncre, MAXT);
         heap_build<true>(heap, ncre); PROF_MARK(7);
-        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter);
+        const SlotClear sc{tn, ncre, slots};
+        slots_clean = true;
+        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, &sc);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
       } else {
         ns_new = need;
         heap_pad_sentinels<false>(heap, ncre, MAXT);
         heap_build<false>(heap, ncre); PROF_MARK(7);
-        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter);
+        const SlotClear sc{tn, ncre, slots};
+        slots_clean = true;
+        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
       }
     }
@@ -1590,8 +1666,7 @@ beam_kernel_mp(const BeamParams p) {
     const Tok *tlast = tok0 + (size_t)(s_cur ^ 1) * MAXT;
     for (int i = tid; i < n_left; i += BEAM_THREADS) {
       const int node = tlast[i].node;
-      __stcg(firstseq + node, 0x7fffffff);
-      __stcg(bestkey + node, 0ull);
+      slots.reset(node);
     }
     __syncthreads();
   }
@@ -1608,9 +1683,9 @@ __global__ void iw_table_kernel(BeamParams p, const int *iso_word, float *iw, in
   iw[(size_t)lw * p.n_iso + p.iso_id[i]] = bigram_prob(p, p.wton[lw], p.wton[w]) + p.cprob[w];
 }
 
-__global__ void fill_slots_kernel(int *firstseq, unsigned long long *bestkey, size_t n) {
+__global__ void fill_slots_kernel(NodeSlot *slots, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { firstseq[i] = 0x7fffffff; bestkey[i] = 0ull; }
+  if (i < n) slots[i] = NodeSlot{0ull, 0x7fffffff, 0};
 }
 
 }  // namespace jb200
@@ -1798,8 +1873,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.tok));
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.order));
-  TRY(dev_alloc(d, (size_t)max_utts * n, &P.firstseq));
-  TRY(dev_alloc(d, (size_t)max_utts * n, &P.bestkey));
+  TRY(dev_alloc(d, (size_t)max_utts * n, &P.slots));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.cand));
   const int n_isoent = std::max(std::max(t->n_iso, P.n_isoarc), 1);
   TRY(dev_alloc(d, (size_t)max_utts * n_isoent, &P.iso));
@@ -1813,10 +1887,22 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
   P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
   P.heap_mode = getenv("JB200_HEAP_MODE") ? atoi(getenv("JB200_HEAP_MODE")) : 0;   // 0 fast sequential (sentinels, speculative loads), 1 lock-step pipelined, 2 lean sequential
+  {
+    // bigram-factoring memo: keys are (word id, successor slot) packed 16+16, so it needs both below 65535
+    int bits = getenv("JB200_LMCACHE_BITS") ? atoi(getenv("JB200_LMCACHE_BITS")) : 21;
+    if (t->n_words >= 65535 || t->n_scword >= 65535 || bits < 8) bits = 0;
+    if (bits > 26) bits = 26;
+    P.lmc_bits = bits; P.lmc = nullptr;
+    if (bits > 0) {
+      TRY(dev_alloc(d, (size_t)1 << bits, &P.lmc));
+      TRYC(cudaMemsetAsync(P.lmc, 0xff, sizeof(unsigned long long) << bits, d->stream));
+    }
+  }
+  P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   {
     size_t tot = (size_t)max_utts * n;
-    fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.firstseq, P.bestkey, tot);
+    fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.slots, tot);
     g_launches.fetch_add(1);
     TRYC(cudaGetLastError());
   }

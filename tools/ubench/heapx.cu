@@ -49,13 +49,67 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
     cur = ncur;                                                                                      \
   }
 
+// two tree levels per round trip: the pairs below BOTH children are requested together with the children
 template <int V>
-__global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int n, int extract, float lose_below,
+__device__ __forceinline__ void extract2(unsigned long long *A, int n, int extract, float lose_below, unsigned long long *outv,
+                                         unsigned &levels_out, unsigned &sink_out) {
+  unsigned levels = 0, sinkacc = 0;
+  const unsigned hb = smem_u32(A);
+  const unsigned capa = hb + (((unsigned)(MAXT >> 1) + 1u) << 4);
+  unsigned mslot = hb + ((unsigned)n << 3);
+  for (int x = 0; x < extract; x++) {
+    unsigned s_lo, s_hi, r_lo, r_hi;
+    unsigned p0, p1, p2, p3, l0, l1, l2, l3, r0, r1, r2, r3;     // children pair, left child's pair, right child's pair
+    lds_one(mslot, s_lo, s_hi);
+    sts_one(mslot, 0xff800000u, 0u);
+    lds_one(hb + 8u, r_lo, r_hi);
+    lds_pair(hb + 16u, p0, p1, p2, p3);
+    lds_pair(hb + 32u, l0, l1, l2, l3);
+    lds_pair(hb + 48u, r0, r1, r2, r3);
+    mslot -= 8u;
+    outv[x] = ((unsigned long long)r_hi << 32) | r_lo;
+    const float sv = __uint_as_float(s_lo);
+    unsigned slot = hb + 8u, cur = hb + 16u;
+    while (true) {
+      // level A
+      const bool ra = __uint_as_float(p0) < __uint_as_float(p2);
+      const unsigned ca_lo = ra ? p2 : p0, ca_hi = ra ? p3 : p1;
+      const unsigned g0 = ra ? r0 : l0, g1 = ra ? r1 : l1, g2 = ra ? r2 : l2, g3 = ra ? r3 : l3;
+      const unsigned ua = (cur << 1) - hb;
+      const unsigned cura = ra ? ua + 16u : ua;                 // pair of the chosen child (what g* holds); may exceed the array
+      // level B
+      const bool rb = __uint_as_float(g0) < __uint_as_float(g2);
+      const unsigned ub = (cura << 1) - hb;
+      const unsigned curb = min(rb ? ub + 16u : ub, capa);
+      const unsigned uc = (curb << 1) - hb;
+      lds_pair(curb, p0, p1, p2, p3);                           // speculative: next round's three pairs
+      lds_pair(min(uc, capa), l0, l1, l2, l3);
+      lds_pair(min(uc + 16u, capa), r0, r1, r2, r3);
+      sinkacc += p0 ^ l0 ^ r0;
+      levels++;
+      if (sv >= __uint_as_float(ca_lo) || __uint_as_float(ca_lo) < lose_below) break;
+      sts_one(slot, ca_lo, ca_hi);
+      slot = cur + (ra ? 8u : 0u);
+      const unsigned cb_lo = rb ? g2 : g0, cb_hi = rb ? g3 : g1;
+      levels++;
+      if (sv >= __uint_as_float(cb_lo) || __uint_as_float(cb_lo) < lose_below) break;
+      sts_one(slot, cb_lo, cb_hi);
+      slot = min(cura, capa) + (rb ? 8u : 0u);
+      cur = curb;
+    }
+    sts_one(slot, s_lo, s_hi);
+  }
+  levels_out = levels; sink_out = sinkacc;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int n, int extract_in, float lose_below,
                                             unsigned long long *outg, long long *res) {
   __shared__ __align__(16) unsigned long long A[MAXT + 4];
   __shared__ unsigned long long outs[1024];
   for (int i = threadIdx.x; i < MAXT + 4; i += blockDim.x) A[i] = (i >= 1 && i <= n) ? init[i] : 0xff800000ull;
   __syncthreads();
+  int extract = extract_in;
   if (threadIdx.x == 0) {
     unsigned long long *outv = (V == 1) ? outs : outg + (size_t)blockIdx.x * 1024;
     unsigned levels = 0, sink = 0, sinkacc = 0;
@@ -63,6 +117,7 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
     const unsigned capa = hb + (((unsigned)(MAXT >> 1) + 1u) << 4);
     unsigned mslot = hb + ((unsigned)n << 3);
     long long t0 = clock64();
+    if (V == 6) { extract2<V>(A, n, extract, lose_below, outv, levels, sinkacc); extract = 0; }
     for (int x = 0; x < extract; x++) {
       unsigned s_lo, s_hi, r_lo, r_hi, x0, x1, y0, y1, z0, z1, w0, w1;
       lds_one(mslot, s_lo, s_hi);
@@ -93,7 +148,7 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
     res[blockIdx.x * 2 + 1] = levels;
   }
   __syncthreads();
-  if (blockIdx.x == 0 && V == 1) for (int i = threadIdx.x; i < extract; i += blockDim.x) outg[i] = outs[i];
+  if (blockIdx.x == 0 && V == 1) for (int i = threadIdx.x; i < extract_in; i += blockDim.x) outg[i] = outs[i];
 }
 
 int main() {
@@ -128,7 +183,7 @@ int main() {
   cudaMalloc(&o, sizeof(unsigned long long) * 1024 * 592); cudaMalloc(&r, sizeof(hr));
   std::vector<unsigned long long> ho(1024);
   for (int blocks : {1, 148, 592}) {
-    for (int v = 0; v < 6; v++) {
+    for (int v = 0; v < 7; v++) {
       for (int rep = 0; rep < 2; rep++) {
         switch (v) {
           case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
@@ -137,6 +192,7 @@ int main() {
           case 3: k<3><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 4: k<4><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 5: k<5><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 6: k<6><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
         }
         cudaDeviceSynchronize();
       }
