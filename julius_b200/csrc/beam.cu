@@ -52,9 +52,10 @@ static constexpr unsigned SEQ_LOCAL = 1u << SEQ_LOCAL_BITS;
 static constexpr int CD_NMAX = 16;
 static constexpr int MAX_WORDS = 150;      // MAXSEQNUM, libsent/include/sent/speech.h:50
 
-struct __align__(16) NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, scid; int out; int pad; };   // 32 B
+struct __align__(16) NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, pad; int scid, out; };   // 32 B; (scid,out) is one aligned 8-byte word
 struct __align__(8) Tok { float score; int node; int tre; int cword; float lscore; int tre_wid; };              // 24 B
 struct __align__(16) Cand { float score; int node; float lscore; int src; };                                     // 16 B
+struct __align__(16) CandB { int tre; int cword; int tre_wid; int out; };                                        // 16 B: what the winner hands to the new token
 struct __align__(16) IsoCand { float score; int e; float lscore; int first_e; };                                 // 16 B
 struct __align__(8) WEnd { int j; int atom; int last_word; float base; int transp2; int nintra; };              // 24 B
 
@@ -92,7 +93,7 @@ struct BeamParams {
   // batch
   const float *rows; int row_stride; const int *frame_off;
   // per-utterance work areas (index = blockIdx.x)
-  Tok *tok; int *order; NodeSlot *slots; Cand *cand; IsoCand *iso; WEnd *wend;
+  Tok *tok; int *order; NodeSlot *slots; Cand *cand; CandB *candb; Tok *surv; IsoCand *iso; WEnd *wend;
   jb200_atom *atoms_raw; int *newidx; int *group0; int *counts;
   const long long *atom_off;
   // compact outputs
@@ -669,6 +670,8 @@ beam_kernel(const BeamParams p) {
   int *ord0 = p.order + (size_t)u * 2 * MAXT;
   const SlotView slots{p.slots + (size_t)u * p.n_nodes};
   Cand *cand = p.cand + (size_t)u * MAXC;
+  CandB *candb = p.candb + (size_t)u * MAXC;
+  Tok *surv = p.surv + (size_t)u * (p.beam + 2);       // the survivors of the previous frame, in visiting order
   IsoCand *iso = p.iso + (size_t)u * max(p.n_iso, 1);
   WEnd *wend = p.wend + (size_t)u * MAXW;
   unsigned *bits = p.bitmask + (size_t)u * (p.maxbits >> 5);
@@ -697,6 +700,7 @@ beam_kernel(const BeamParams p) {
     tk.lscore = ll; tk.tre = -1; tk.cword = -1; tk.tre_wid = -1; tk.node = node;
     tk.score = outprob_style(p, p.rows + (size_t)f_begin * p.row_stride, nr.out, -1) + ll;
     tok0[0] = tk;
+    surv[0] = tk;
     ord0[0] = 0;
     s_ns = 1;
     counts[0] = 1; counts[1] = 1;
@@ -738,7 +742,7 @@ beam_kernel(const BeamParams p) {
         int nin = 0, is_we = 0, is_tr = 0;
         Tok tk; NodeRec nr;
         if (j < ns) {
-          tk = tl[ordl[j]];
+          tk = surv[j];
           nr = p.nodes[tk.node];
           const bool valid = (tk.score > JB200_LOG_ZERO) && !(tk.score < thr);
           if (valid) {
@@ -802,7 +806,7 @@ beam_kernel(const BeamParams p) {
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= c) lo = mid; else hi = mid; }
       const int j = lo;
       int k = c - offs[j];
-      const Tok tk = tl[ordl[j]];
+      const Tok tk = surv[j];
       const NodeRec nr = p.nodes[tk.node];
       int next; float pa;
       const int has_self = (nr.self_a != JB200_LOG_ZERO), has_next = (nr.next_a != JB200_LOG_ZERO);
@@ -811,8 +815,11 @@ beam_kernel(const BeamParams p) {
       else { const int a = k - has_self - has_next; next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
       float tmpsum = tk.score + pa;
       float lsc = JB200_LOG_ZERO;
+      int out_next = nr.out;
       if (next != tk.node) {
-        const int scid = p.nodes[next].scid;
+        const int2 so = __ldg(reinterpret_cast<const int2 *>(&p.nodes[next].scid));
+        const int scid = so.x;
+        out_next = so.y;
         if (scid != 0) {
           lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
           tmpsum -= tk.lscore;
@@ -822,6 +829,8 @@ beam_kernel(const BeamParams p) {
       if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
       Cand cd; cd.score = tmpsum; cd.node = next; cd.lscore = lsc; cd.src = j;
       cand[c] = cd;
+      CandB cb; cb.tre = tk.tre; cb.cword = tk.cword; cb.tre_wid = tk.tre_wid; cb.out = out_next;
+      candb[c] = cb;
       if (tmpsum > JB200_LOG_ZERO) {
         const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
         cand_atomics(slots, next, tmpsum, seq, seq);
@@ -936,26 +945,30 @@ beam_kernel(const BeamParams p) {
       const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
       const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
       Tok nt; nt.node = node;
+      int out;
       if (j == ns) {                                    // factoring pass
         const float lsc = __ldg(p.shared_f + local) * p.lm_weight + p.lm_penalty;
         float tmpsum = wbest.base; tmpsum += lsc;
         if (wbest.transp2) tmpsum += p.lm_penalty_trans;
         nt.score = tmpsum; nt.lscore = lsc; nt.tre = wbest.atom; nt.cword = wbest.last_word;
         nt.tre_wid = araw[wbest.atom].wid;
+        out = p.nodes[node].out;
       } else {
         const int c0 = offs[j], nin = offs[j + 1] - c0;
-        if (local < nin) {                              // word-internal candidate
+        if (local < nin) {                              // word-internal candidate: everything travels with it
           const Cand cd = cand[c0 + local];
-          const Tok src = tl[ordl[j]];
-          nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = src.tre; nt.cword = src.cword; nt.tre_wid = src.tre_wid;
+          const CandB cb = candb[c0 + local];
+          nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = cb.tre; nt.cword = cb.cword; nt.tre_wid = cb.tre_wid;
+          out = cb.out;
         } else {                                        // isolated-root candidate
           const IsoCand ic = iso[local - nin];
           const WEnd w = wend[ic.e];
           nt.score = ic.score; nt.lscore = ic.lscore; nt.tre = w.atom; nt.cword = w.last_word;
           nt.tre_wid = araw[w.atom].wid;
+          out = p.nodes[node].out;
         }
       }
-      nt.score += outprob_style(p, row, p.nodes[node].out, nt.tre_wid);
+      nt.score += outprob_style(p, row, out, nt.tre_wid);
       tn[r] = nt;
       heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
       atomicMax(&s_pmaxkey, fkey(nt.score));
@@ -1076,6 +1089,8 @@ beam_kernel(const BeamParams p) {
         }
       }
     }
+    // the survivors in visiting order, compact (every thread re-reads the order entries it wrote itself)
+    for (int k = tid; k < ns_new; k += BEAM_THREADS) surv[k] = tn[ordn[k]];
     PROF_MARK(6);
     if (tid == 0) {
       counts[2 * t] = ncre; counts[2 * t + 1] = ns_new;
@@ -1103,7 +1118,7 @@ beam_kernel(const BeamParams p) {
     for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
       const int j = j0 + tid;
       int is_we = 0; Tok tk; int stend = -1;
-      if (j < ns) { tk = tl[ordl[j]]; stend = p.nodes[tk.node].stend; is_we = (stend >= 0); }
+      if (j < ns) { tk = surv[j]; stend = p.nodes[tk.node].stend; is_we = (stend >= 0); }
       int tot;
       const int oa = block_excl_scan(is_we, s_warp, &tot);
       if (is_we) {
@@ -1875,6 +1890,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.order));
   TRY(dev_alloc(d, (size_t)max_utts * n, &P.slots));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.cand));
+  TRY(dev_alloc(d, (size_t)max_utts * P.maxc, &P.candb));
+  TRY(dev_alloc(d, (size_t)max_utts * (t->beam_width + 2), &P.surv));
   const int n_isoent = std::max(std::max(t->n_iso, P.n_isoarc), 1);
   TRY(dev_alloc(d, (size_t)max_utts * n_isoent, &P.iso));
   TRY(dev_alloc(d, (size_t)max_utts * P.maxw, &P.wend));
