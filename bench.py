@@ -328,9 +328,10 @@ def product_main(a):
         created_per_frame = float(counts[:, 0].mean())
         gmm_bytes = M_total * ALG_GMM_BYTES_PER_GAUSS + B * T * (D * 4 + 4 * S)
         beam_bytes = B * T * tokens_per_frame * ALG_BEAM_BYTES_PER_TOKEN
+        beam_name = "beam_kernel_mp" if int(ds.tree.multipath) else "beam_kernel"
         score_name = "dnn_gemm_kernel (x%d layers)" % ds.dnn.n_layers if use_dnn else "gmm_score_kernel"
         if bm_ms >= gmm_ms:
-            dom, dom_ms, dom_bytes = "beam_kernel", bm_ms, beam_bytes
+            dom, dom_ms, dom_bytes = beam_name, bm_ms, beam_bytes
         else:
             dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
         ach = dom_bytes / (dom_ms / 1000.0) / 1e9
@@ -358,7 +359,7 @@ def product_main(a):
                        "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": {score_name: gmm_ms, "beam_kernel": bm_ms},
+                         "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
                          "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
                          "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_extract", "heap_build"), phase)},
