@@ -335,6 +335,15 @@ def product_main(a):
         else:
             dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
         ach = dom_bytes / (dom_ms / 1000.0) / 1e9
+        # DRAM traffic of the dominant kernel per launch, scaled from the committed ncu --set full capture
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tfile):
+            tj = json.load(open(tfile))
+            if dom == "beam_kernel" and "beam_kernel" in tj:
+                traffic = tj["beam_kernel"]["bytes_per_utterance_frame"] * B * T
+            elif dom == "gmm_score_kernel" and "gmm_score_kernel" in tj:
+                traffic = tj["gmm_score_kernel"]["bytes_per_frame"] * B * T
         tensor = None
         if use_dnn:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -358,7 +367,8 @@ def product_main(a):
                        "l2": "per-step working set (score matrix %.1f GB) exceeds L2; input batch alternates" % (B * T * S * 4 / 1e9),
                        "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, scaled from profiles/ncu_traffic.json)",
+                         "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
                          "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
                          "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
