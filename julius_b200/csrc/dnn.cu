@@ -12,7 +12,8 @@
 // (x = hi + lo, 16 mantissa bits) and each k-block issues three MMAs into the same fp32
 // accumulator in TMEM:  hi.hi + hi.lo + lo.hi   (the dropped lo.lo term is 2^-16 relative).
 //
-// Kernel anatomy (sm_100a): 192 threads = warp 0 TMA producer, warp 1 tcgen05.mma issuer,
+// Kernel anatomy (sm_100a), dnn_gemm_persistent<256> by default (dnn_gemm_kernel = the one-tile-per-CTA
+// first version, JB200_DNN_KERNEL=0): 192 threads = warp 0 TMA producer, warp 1 tcgen05.mma issuer,
 // warps 2-5 epilogue (each owns the TMEM lane quarter warp_idx%4).  Operand tiles
 // 128 x 64 bf16 (K-major, 128-byte swizzle) arrive by cp.async.bulk.tensor (TMA) into a 3-stage
 // shared-memory ring guarded by full/empty mbarriers; the 128 x 128 fp32 accumulator lives in
@@ -211,6 +212,159 @@ dnn_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
 }
 
+// ---- persistent variant -----------------------------------------------------------------------------
+// One CTA per SM walks the output tiles (column blocks fastest, so the CTAs that run side by side share the
+// activation rows in L2); the accumulator is double-buffered in TMEM, so the four epilogue warps drain tile i
+// (tcgen05.ld, bias, table logistic, bf16 hi/lo split, stores) while the MMA warp is already filling tile i+1
+// and the TMA warp runs ahead through the shared-memory ring.  BN_ = 128 (3 stages of 64 KB) or 256 (2 stages of
+// 96 KB: a 128x256 tile moves 1.5x the bytes for 2x the flops -- the kernel is bound by the L2 -> shared-memory
+// path).
+template <int BN_>
+struct PersistentCfg {
+  static constexpr int STAGES_ = (BN_ == 128) ? 3 : 2;
+  static constexpr int B_TILE = BN_ * BK * 2;
+  static constexpr int STAGE = 2 * TILE_BYTES + 2 * B_TILE;     // A_hi A_lo B_hi B_lo
+  static constexpr int SMEM = STAGES_ * STAGE + 1024 + 256;
+};
+
+template <int BN_>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dnn_gemm_persistent(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    const GemmArgs g) {
+  using Cfg = PersistentCfg<BN_>;
+  constexpr int S = Cfg::STAGES_;
+  extern __shared__ unsigned char dsm_raw[];
+  unsigned char *dsm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(dsm + S * Cfg::STAGE);
+  uint64_t *empty = full + S;
+  uint64_t *tmem_full = empty + S;          // [2]
+  uint64_t *tmem_empty = tmem_full + 2;     // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (g.K + BK - 1) / BK;
+  const int n_nblk = (g.N + BN_ - 1) / BN_, n_mblk = (g.M + BM - 1) / BM;
+  const int n_tiles = n_nblk * n_mblk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN_)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_nblk) * BM, n0 = (tile % n_nblk) * BN_;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          unsigned char *st = dsm + s * Cfg::STAGE;
+          mbar_expect_tx(&full[s], Cfg::STAGE);
+          tma_load_2d(st, &map_a_hi, &full[s], kb * BK, m0);
+          tma_load_2d(st + TILE_BYTES, &map_a_lo, &full[s], kb * BK, m0);
+          unsigned char *bh = st + 2 * TILE_BYTES, *bl = bh + Cfg::B_TILE;
+#pragma unroll
+          for (int h = 0; h < BN_ / 128; h++) {                 // the weight maps have 128-row boxes
+            tma_load_2d(bh + h * TILE_BYTES, &map_b_hi, &full[s], kb * BK, n0 + h * 128);
+            tma_load_2d(bl + h * TILE_BYTES, &map_b_lo, &full[s], kb * BK, n0 + h * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+        const int b = i & 1;
+        mbar_wait(&tmem_empty[b], (uint32_t)((i >> 1) & 1) ^ 1u);    // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(b * BN_);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          unsigned char *st = dsm + s * Cfg::STAGE;
+          const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_BYTES);
+          const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 2 * TILE_BYTES + Cfg::B_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            tc_mma_bf16(acc, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+            tc_mma_bf16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+            tc_mma_bf16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tmem_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, i++) {
+      const int b = i & 1;
+      const int m0 = (tile / n_nblk) * BM, n0 = (tile % n_nblk) * BN_;
+      mbar_wait(&tmem_full[b], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN_ / 32; c++) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN_ + c * 32), r);
+        const int col0 = n0 + c * 32;
+        if (row < g.M) {
+          if (g.last) {
+            float *dst = g.logits + (size_t)row * g.ld_logits + col0;
+#pragma unroll
+            for (int e = 0; e < 32; e++)
+              if (col0 + e < g.N) dst[e] = __uint_as_float(r[e]) + __ldg(g.bias + col0 + e);
+          } else {
+            __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+              float v = 0.0f;
+              if (col0 + e < g.N) v = logistic_ref(__uint_as_float(r[e]) + __ldg(g.bias + col0 + e), g.logistic);
+              const __nv_bfloat16 h = __float2bfloat16_rn(v);
+              hi[e] = h;
+              lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+            uint4 *dh = reinterpret_cast<uint4 *>(g.out_hi + (size_t)row * g.ld_out + col0);
+            uint4 *dl = reinterpret_cast<uint4 *>(g.out_lo + (size_t)row * g.ld_out + col0);
+#pragma unroll
+            for (int v4 = 0; v4 < 4; v4++)
+              if (col0 + v4 * 8 < g.ld_out) { dh[v4] = reinterpret_cast<const uint4 *>(hi)[v4]; dl[v4] = reinterpret_cast<const uint4 *>(lo)[v4]; }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[b]);               // 4 arrivals (one per epilogue warp) free the accumulator
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BN_)) : "memory");
+  }
+}
+
 // fp32 [M][K] -> bf16 hi/lo [M][ld] (zero padded)
 __global__ void split_bf16_kernel(const float *__restrict__ src, int M, int K, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int ld) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,7 +441,7 @@ struct jb200_dnn {
   PFN_encodeTiled encode = nullptr;
   cudaStream_t stream = nullptr;
   // batch buffers
-  int cap_frames = 0, max_width = 0, ld_logits = 0;
+  int cap_frames = 0, max_width = 0, ld_logits = 0, n_sm = 0, variant = 256;
   float *d_in = nullptr, *d_logits = nullptr, *d_rows = nullptr;
   __nv_bfloat16 *act_hi[2] = {nullptr, nullptr}, *act_lo[2] = {nullptr, nullptr};
 };
@@ -367,6 +521,10 @@ extern "C" int jb200_dnn_create(const jb200_dnn_desc *d, int device, jb200_dnn *
   }
   h->ld_logits = (d->out_dim + 3) & ~3;
   JB_CUDA(cudaFuncSetAttribute(dnn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  JB_CUDA(cudaFuncSetAttribute(dnn_gemm_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistentCfg<128>::SMEM));
+  JB_CUDA(cudaFuncSetAttribute(dnn_gemm_persistent<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistentCfg<256>::SMEM));
+  h->n_sm = prop.multiProcessorCount;
+  h->variant = getenv("JB200_DNN_KERNEL") ? atoi(getenv("JB200_DNN_KERNEL")) : 256;   // 0 one tile per CTA, 128 / 256 persistent
   *out = h;
   return JB200_OK;
 }
@@ -414,8 +572,16 @@ int dnn_forward_device(jb200_dnn *h, const float *d_in, int T, float *d_rows, in
     g.out_hi = h->act_hi[cur ^ 1]; g.out_lo = h->act_lo[cur ^ 1];
     g.ld_out = g.last ? 0 : h->L[l + 1].ld_in;
     g.logits = h->d_logits; g.ld_logits = h->ld_logits;
-    dim3 grid((L.out + BN - 1) / BN, (T + BM - 1) / BM);
-    dnn_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
+    if (h->variant == 0) {
+      dim3 grid((L.out + BN - 1) / BN, (T + BM - 1) / BM);
+      dnn_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
+    } else if (h->variant == 128) {
+      const int tiles = ((L.out + 127) / 128) * ((T + BM - 1) / BM);
+      dnn_gemm_persistent<128><<<std::min(tiles, h->n_sm), GEMM_THREADS, PersistentCfg<128>::SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
+    } else {
+      const int tiles = ((L.out + 255) / 256) * ((T + BM - 1) / BM);
+      dnn_gemm_persistent<256><<<std::min(tiles, h->n_sm), GEMM_THREADS, PersistentCfg<256>::SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
+    }
     JB_LAUNCH_CHECK();
     cur ^= 1;
   }
