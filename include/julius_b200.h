@@ -147,7 +147,7 @@ int jb200_decoder_last_timing(jb200_decoder *d, float ms[4]);
 int jb200_decoder_sync_timing(jb200_decoder *d);
 /* bytes moved device->host by the last fetch (results + atoms + words) */
 int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d);
-/* how often (frames, since create) the pipelined heap replay had to fall back to the sequential one */
+/* how often (frames, since create) the beam cut had to fall back to the plain sequential replay (0 unless forced) */
 int64_t jb200_decoder_misspeculations(jb200_decoder *d);
 /* beam-cut replay counters since create: out[0] fall-backs, out[1] heap levels walked, out[2] extractions */
 int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]);

@@ -18,13 +18,14 @@
 //     the factoring pass gets j = n_survivors;
 //   * per destination node:  first arrival   = atomicMin(seq)          (who creates the token)
 //                            winning content = atomicMax(score, ~seq)  (strict '<' keeps the incumbent)
-//   * new-token numbering = rank of the creators' seq (bitonic sort in shared memory);
+//   * new-token numbering = rank of the creators in arrival order (one bit per candidate position, popcount prefix);
 //   * inter-word transitions into the "isolated" roots are pre-reduced per root over the frame's
 //     word-end tokens (max is associative; first/winner seqs are carried along); the per-last-word
 //     bigram rows the reference caches lazily (iw_sc_cache) are tabulated once at create time;
 //   * the beam cut replays the reference's heap select exactly: bottom-up heap construction is
 //     level-parallel (siftdowns of one level touch disjoint subtrees), the extractions are
-//     replayed by one thread on a shared-memory heap.
+//     replayed by one thread on a shared-memory heap (heap_extract_fast) while the other warps
+//     reset the per-node slots for the next frame.
 // All frames of an utterance run inside one kernel launch; tokens, node slots and candidates
 // live in per-utterance global scratch (L2 resident), the sort/heap array in shared memory.
 //
@@ -102,7 +103,7 @@ struct BeamParams {
   long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
   unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
   unsigned long long *outv;          // per-utterance extracted heap roots [beam+1]
-  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, heap_mode, prof_fine;
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine;
   unsigned long long *lmc; int lmc_bits;      // memo of max_successor_prob, 2^lmc_bits entries (0 = off)
   int maxt, maxc, maxw, maxbits;
 };
@@ -360,45 +361,7 @@ __device__ __forceinline__ void sts_one(unsigned addr, unsigned x0, unsigned x1)
   asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(x0), "r"(x1) : "memory");
 }
 
-// Lean single-thread extraction replay: explicit shared-window addressing, one aligned 16-byte load per
-// tree level.  Max-heap selects stop as soon as the larger child is below `lose_below` (see the note on
-// winners and losers above heap_extract_pipelined): ~8.5 instead of ~11.2 levels per extraction.
-template <bool MAXHEAP>
-__device__ void heap_extract_lean(unsigned long long *A, const int n, const int extract, const float lose_below) {
-  if (threadIdx.x == 0) {
-    const unsigned hb = smem_u32(A);
-    int m = n;
-    unsigned r0, r1;
-    lds_one(hb + 8u, r0, r1);                         // current root
-    for (int x = 0; x < extract; x++) {
-      unsigned s_lo, s_hi;
-      lds_one(hb + ((unsigned)m << 3), s_lo, s_hi);
-      sts_one(hb + ((unsigned)m << 3), r0, r1);       // A[m] = A[1]
-      m--;
-      if (m < 1) break;
-      const float sv = __uint_as_float(s_lo);
-      unsigned par = 1u;
-      bool first = true;
-      while (true) {
-        const unsigned child = par << 1;
-        if ((int)child > m) break;
-        unsigned x0, x1, y0, y1;
-        lds_pair(hb + (par << 4), x0, x1, y0, y1);
-        const bool right = ((int)child < m) && hcmp<MAXHEAP>(__uint_as_float(x0), __uint_as_float(y0));
-        const unsigned c_lo = right ? y0 : x0, c_hi = right ? y1 : x1;
-        if (hstop<MAXHEAP>(sv, __uint_as_float(c_lo)) || (MAXHEAP && __uint_as_float(c_lo) < lose_below)) break;
-        sts_one(hb + (par << 3), c_lo, c_hi);
-        if (first) { r0 = c_lo; r1 = c_hi; first = false; }   // new root value
-        par = child + (right ? 1u : 0u);
-      }
-      sts_one(hb + (par << 3), s_lo, s_hi);
-      if (first) { r0 = s_lo; r1 = s_hi; }
-    }
-  }
-  __syncthreads();
-}
-
-// Fast single-thread extraction replay.  Same comparisons as heap_extract_lean, arranged so that the
+// Fast single-thread extraction replay.  Same comparisons as heap_extract_seq, arranged so that the
 // loop-carried dependence of one tree level is  LDS.128 -> compare -> select next address -> LDS.128 :
 //   * a freed tail slot is overwritten with a sentinel (-inf for the max-heap, +inf for the min-heap) and
 //     so is everything between n+1 and the last child slot (heap_pad_sentinels), which makes both bounds
@@ -494,79 +457,6 @@ __device__ void heap_extract_fast(unsigned long long *A, const int n, const int 
   __syncthreads();
 }
 #undef JB_HEAP_LEVEL
-
-// Pipelined extraction replay, warp 0, lock-step.  Lane k of the warp owns the extractions x with
-// x mod NL == k; every extraction in flight advances exactly one tree level per "tick" and a new one
-// starts at least two ticks after the previous one, so extraction x always works two levels above x-1:
-// it reads level L+1 one tick after x-1 wrote it and never touches a level x-1 is touching in the same
-// tick.  The only other coupling is at the bottom-right corner of the heap:
-//   * the extracted roots are NOT written into the tail slots while older extractions are in flight
-//     (those slots still belong to the older, larger heaps); they go to `outv`, the caller places them;
-//   * extraction x takes s = A[n-x] when it starts.  Sequential execution would hand it a different
-//     value only if an older extraction ends its sift exactly in that slot, and an extraction can only
-//     get there through the slot's ancestors.  So x does not start while an extraction in flight sits
-//     on an ancestor of slot n-x (a stall of a tick or two, ~0.6 tick per extraction on average);
-//     once no one does, A[n-x] is final.  No speculation, no rollback.
-// Max-heap ("upward") selects only: an element that is not among the `extract` largest can never be
-// extracted, and the order in which the winners come out does not depend on how the losers are
-// arranged among themselves (a loser only ever moves when no winner is below the hole, and a re-inserted
-// loser sinks below every winner whatever its value).  So the sift stops as soon as the larger child is
-// below `lose_below`, any lower bound of the extract-th largest score.
-// A single thread needs ~90 cycles per tree level (dependent-issue latency); the lock-step pipeline
-// retires one extraction every ~2.6 ticks instead of every ~11 levels.
-// (CPU model of exactly this schedule vs the sequential loop: tools/heapsim.cpp.)  Ends with a barrier.
-template <bool MAXHEAP>
-__device__ void heap_extract_pipelined(unsigned long long *A, const int n, const int extract, unsigned long long *outv,
-                                       const float lose_below /* max-heap only: children below this never win */) {
-  constexpr int NL = 16;
-  if (threadIdx.x < 32) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    bool act = false;
-    int par = 1, m = 0, lvl = 0;
-    unsigned long long s = 0ull; float sv = 0.0f;
-    int next_x = 0, wait = 0;
-    while (true) {
-      // (1) one level step for every extraction in flight
-      if (act) {
-        const int child = par * 2;
-        unsigned long long put = s;
-        bool stop = true;
-        if (child <= m) {
-          const ulonglong2 pr = *reinterpret_cast<const ulonglong2 *>(A + child);
-          const bool right = (child < m) && hcmp<MAXHEAP>(hval(pr.x), hval(pr.y));
-          const unsigned long long c = right ? pr.y : pr.x;
-          if (!hstop<MAXHEAP>(sv, hval(c)) && !(MAXHEAP && hval(c) < lose_below)) { stop = false; put = c; }
-          A[par] = put;
-          if (!stop) { par = child + (right ? 1 : 0); lvl++; }
-        } else A[par] = put;
-        act = !stop;
-      }
-      __syncwarp();
-      // (2) start the next extraction: >= 2 ticks after the previous start, its lane free, and nobody
-      //     in flight on an ancestor of its slot
-      if (--wait <= 0) {
-        if (next_x < extract) {
-          const int ms = n - next_x;
-          const int dms = 31 - __clz(ms);
-          const int ln = next_x & (NL - 1);
-          const bool blocks = act && ((lane == ln) || (dms >= lvl && (ms >> (dms - lvl)) == par));
-          if (!__any_sync(full, blocks)) {
-            if (lane == ln) {
-              s = A[ms]; sv = hval(s);
-              outv[next_x] = A[1];
-              m = ms - 1; par = 1; lvl = 0;
-              act = (m >= 1);
-            }
-            next_x++; wait = 2;
-          }
-        } else if (!__any_sync(full, act)) break;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-}
 
 // phase cycle accounting (thread 0 only; negligible cost)
 #define PROF_MARK(k) do { if (tid == 0) { long long _n = clock64(); s_prof[k] += _n - s_tprev; s_tprev = _n; } } while (0)
@@ -1006,8 +896,7 @@ beam_kernel(const BeamParams p) {
         // the node slots of this frame are dead from here on: warps 1.. reset them for the next frame while
         // thread 0 is busy with the extraction replay (SlotClear, run inside heap_extract_fast*)
         const SlotClear sc{tn, ncre, slots};
-        const bool fastpath = !p.force_seq_heap && (p.heap_mode == 0);
-        if (!fastpath) sc.run((int)threadIdx.x, BEAM_THREADS);
+        if (p.force_seq_heap) sc.run((int)threadIdx.x, BEAM_THREADS);
         slots_clean = true;
         if (!p.force_seq_heap) {
           if (upward) {
@@ -1051,18 +940,11 @@ beam_kernel(const BeamParams p) {
             const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
             heap_pad_sentinels<true>(heap, ncre, MAXT);
             heap_build<true>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter, &sc);
-            else if (p.heap_mode == 2) {
-              heap_extract_lean<true>(heap, ncre, extract, lose_below);
-              for (int k = tid; k < extract; k += BEAM_THREADS) outv[k] = heap[ncre - k];   // same convention as the other replays
-              __syncthreads();
-            } else heap_extract_pipelined<true>(heap, ncre, extract, outv, lose_below);
+            heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter, &sc);
           } else {
             heap_pad_sentinels<false>(heap, ncre, MAXT);
             heap_build<false>(heap, ncre); PROF_MARK(7);
-            if (p.heap_mode == 0) heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
-            else if (p.heap_mode == 2) heap_extract_lean<false>(heap, ncre, extract, -INFINITY);
-            else heap_extract_pipelined<false>(heap, ncre, extract, outv, -INFINITY);
+            heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
           }
           ok = true;
           if (ok) {
@@ -1903,7 +1785,6 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMemset(P.misspec_counter, 0, 4 * sizeof(unsigned long long)));
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
   P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
-  P.heap_mode = getenv("JB200_HEAP_MODE") ? atoi(getenv("JB200_HEAP_MODE")) : 0;   // 0 fast sequential (sentinels, speculative loads), 1 lock-step pipelined, 2 lean sequential
   {
     // bigram-factoring memo: keys are (word id, successor slot) packed 16+16, so it needs both below 65535
     int bits = getenv("JB200_LMCACHE_BITS") ? atoi(getenv("JB200_LMCACHE_BITS")) : 21;

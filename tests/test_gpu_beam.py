@@ -101,9 +101,10 @@ def test_capacity_errors_are_loud():
         dec.decode([g.feats[0]])          # 150 frames > 64
 
 
-def test_pipelined_heap_replay_agrees_with_sequential_replay(monkeypatch):
-    """JB200_CHECK_HEAP=1 makes the kernel run BOTH heap replays every frame and flag any difference
-    in the survivor order (overflow code 4)."""
+def test_fast_heap_replay_agrees_with_sequential_replay(monkeypatch):
+    """JB200_CHECK_HEAP=1 makes the kernel run BOTH heap replays every frame (the sentinel/speculative-load
+    one with the loser cut, and the plain in-place one) and flag any difference in the survivor order
+    (overflow code 4)."""
     monkeypatch.setenv("JB200_CHECK_HEAP", "1")
     for case in ("small_b100", "small_safe"):
         g = Golden(case)

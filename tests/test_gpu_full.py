@@ -86,7 +86,7 @@ def test_fast_mode_scores_within_tolerance_and_decodes(full):
 
 
 def test_full_size_heap_self_check(monkeypatch, oracle_lib):
-    """beam 800 over ~2400 tokens per frame: pipelined vs sequential heap replay on every frame."""
+    """beam 800 over ~2400 tokens per frame: fast vs plain sequential heap replay on every frame."""
     if not workload.ready(NAME):
         pytest.skip("workloads/tri20k not prepared")
     monkeypatch.setenv("JB200_CHECK_HEAP", "1")
