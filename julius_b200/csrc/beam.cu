@@ -1765,7 +1765,10 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     }
   }
   // work areas
-  int maxt = (4 * t->beam_width + t->n_start + 64 + 3) & ~3;   // the reference starts at 2*beam+startnum and grows on demand; we size for 4*beam and flag overflow
+  // the reference starts at 2*beam+startnum tokens and grows on demand; we size once and flag overflow.  Seen on the
+  // 20k-word tree: 4.6*beam at -b 800 (of which startnum = 1375 root tokens), 4.7*beam at -b 4000.  The array lives
+  // in shared memory, and what it takes is lost to L1 (5*beam+startnum at -b 800 costs 30 % of the kernel's speed).
+  int maxt = (std::max(4 * t->beam_width + t->n_start, 5 * t->beam_width) + 64 + 3) & ~3;
   if (const char *e = getenv("JB200_MAXT")) maxt = (std::max(atoi(e), 64) + 3) & ~3;
   P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.tok));

@@ -127,3 +127,26 @@ def test_other_baseline_configs_end_to_end_vs_oracle(name, frames, oracle_lib):
         ok, why = atoms_equal(r["atoms"], o["atoms"])
         assert ok, why
         assert r["words"] == o["words"] and r["status"] == o["status"]
+
+
+@pytest.mark.parametrize("name", ["tri20k", "tri20k_mp"])
+def test_wide_beam_4000_vs_oracle(name, oracle_lib):
+    """BASELINE.json configs[4] flavour: -b 4000 on the 20k-word tree (normal and multipath).  The heap-select
+    array alone is 140 KB of shared memory, one utterance per SM; ~9000 tokens are created per frame."""
+    if not workload.ready(name):
+        pytest.skip(f"workloads/{name} not prepared")
+    blob = refdump.load_blob(workload.path(name, "model.jb2m"))
+    ds = desc.Descriptors(blob)
+    ds.tree.beam_width = 4000
+    m = workload.synth_model(name)
+    am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(ds, am, max_utts=2, max_frames=2 * 120)
+    feats = workload.sample_batch(m, 2, 120, seed=91)
+    res = dec.decode(feats)
+    for x, r in zip(feats, res):
+        o = oracle_lib.beam_decode(ds, oracle_lib.gmm_score(ds, x), trace=True)
+        assert r["overflow"] == 0
+        ok, why = atoms_equal(r["atoms"], o["atoms"])
+        assert ok, why
+        assert r["words"] == o["words"] and r["status"] == o["status"]
+    assert max(c[1] for c in o["trace"]) > 800      # the wide beam was actually used
