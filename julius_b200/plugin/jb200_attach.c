@@ -12,6 +12,7 @@
  * It also provides the calcmix hook set so that "-gprune jb200" is a valid jconf value
  * (libjulius/src/plugin.c:336-354, contract plugin/calcmix.c:226-323): per-Gaussian ln scores of the
  * current frame come from the GPU (jb200_gmm_gauss_host), one device call per frame, sliced per state.
+ * JB200_ATTACH=calcmix attaches only this hook (no cache fill), JB200_ATTACH=1 the whole-utterance scoring.
  * JB200_GMM_MODE=fast selects the FMA/exact-LSE arithmetic (<=1e-4) instead of the bit-exact one.
  */
 #include <julius/juliuslib.h>
@@ -54,8 +55,12 @@ static void on_pass1_begin(Recog *recog, void *dummy) {
   wrk->OP_last_time = -1;
 }
 
+/* calcmix-only attach: a new utterance must not reuse the last utterance's frame of Gaussian scores */
+static void on_pass1_begin_calcmix(Recog *recog, void *dummy) { g_gauss_time = -2; }
+
 int jb200_attach(Recog *recog, jb200_blob *b) {
   const char *mode = getenv("JB200_GMM_MODE");
+  const char *how = getenv("JB200_ATTACH");
   int rc;
   if (jb200_api_load(&g_api, (void *)&jb200_attach) != 0) return -1;
   if (jb200_dnn_from_blob(b, &g_dd) == 0) {
@@ -66,6 +71,12 @@ int jb200_attach(Recog *recog, jb200_blob *b) {
     rc = g_api.gmm_create(&g_gd, 0, (mode && strcmp(mode, "fast") == 0) ? JB200_GMM_FAST : JB200_GMM_EXACT, &g_gmm);
   }
   if (rc != 0) { jlog("ERROR: jb200: cannot create the GPU scorer: %s\n", g_api.last_error()); return -1; }
+  if (how && strcmp(how, "calcmix") == 0) {
+    /* only the -gprune jb200 surface: the host keeps calling outprob_state -> calc_mix -> calcmix() */
+    callback_add(recog, CALLBACK_EVENT_PASS1_BEGIN, on_pass1_begin_calcmix, NULL);
+    jlog("STAT: jb200: GPU Gaussian scoring attached behind the calcmix hook (-gprune jb200)\n");
+    return 0;
+  }
   callback_add(recog, CALLBACK_EVENT_PASS1_BEGIN, on_pass1_begin, NULL);
   jlog("STAT: jb200: GPU acoustic scoring attached (%s)\n", g_dnn ? "DNN, tensor cores" : "GMM");
   return 0;

@@ -455,7 +455,8 @@ int startup(void *data) {
   const char *attach = getenv("JB200_ATTACH");
   jb200_blob *b;
   int rc;
-  if (path == NULL && (attach == NULL || atoi(attach) == 0)) return 0;
+  const int want_attach = attach != NULL && (atoi(attach) != 0 || strcmp(attach, "calcmix") == 0);
+  if (path == NULL && !want_attach) return 0;
   b = (jb200_blob *)malloc(sizeof(jb200_blob));
   jb200_blob_init(b);
   rc = jb200_flatten_recog(recog, b);
@@ -464,7 +465,7 @@ int startup(void *data) {
     if (rc == 0) jlog("STAT: jb200: flattened model written to %s (%d arrays)\n", path, b->n);
     else jlog("ERROR: jb200: cannot write %s\n", path);
   }
-  if (rc == 0 && attach != NULL && atoi(attach) != 0) return jb200_attach(recog, b);   /* keeps the blob alive */
+  if (rc == 0 && want_attach) return jb200_attach(recog, b);   /* keeps the blob alive */
   jb200_blob_free(b);
   free(b);
   return rc;

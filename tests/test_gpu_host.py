@@ -83,3 +83,20 @@ def test_full_two_pass_recognition_is_unchanged_by_either_boundary(case, tmp_pat
     _, c = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], two_pass=True, dump="c.jrf", binary=ffi.JREF_GPU,
                        env_extra={"JB200_ATTACH": "1"})
     assert _results(c) == want
+
+
+def test_calcmix_hook_equals_gprune_none(tmp_path):
+    """The jconf surface `-gprune jb200` (plugin calcmix hook set, plugin.c:336-354): the host keeps its own
+    outprob_state -> calc_mix path and asks the plugin for the per-Gaussian scores of the current frame, which come
+    from the GPU (jb200_gmm_gauss_host).  No pruning is applied, so the run must equal stock `-gprune none`."""
+    from oracle import ffi
+    g, d, files = _prepare("tiny", tmp_path)
+    dump0, _ = ffi.run_ref(d, files, extra_args=["-gprune", "none"], dump="none.jrf")
+    dump1, out = ffi.run_ref(d, files, extra_args=["-gprune", "jb200"], dump="hook.jrf", env_extra={"JB200_ATTACH": "calcmix"})
+    want, got = refdump.load_refdump(dump0), refdump.load_refdump(dump1)
+    assert len(want) == len(got) == len(files)
+    for u, v in zip(want, got):
+        assert np.array_equal(u.outprob.view(np.uint32), v.outprob.view(np.uint32))
+        ok, why = atoms_equal(v.atoms, u.atoms)
+        assert ok, why
+        assert u.words == v.words and np.float32(u.score) == np.float32(v.score)
