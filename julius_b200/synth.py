@@ -45,6 +45,7 @@ class SynthConfig:
     monophone: bool = False    # context-independent AM (config[0])
     one_phone_words: int = 0   # number of 1-phone words (exercise AS_LRSET)
     sp_model: bool = False     # add a 1-state tee model "sp" (skip transition) for -iwsp; forces multipath
+    transparent_words: int = 0 # the first k words get a {..} output string: transparent to the LM context (fillers)
 
     @staticmethod
     def preset(name: str) -> "SynthConfig":
@@ -57,6 +58,9 @@ class SynthConfig:
         if name == "small_sp":   # "small" plus a short-pause tee model (-iwsp, multipath by necessity)
             c = SynthConfig.preset("small")
             return dataclasses.replace(c, name="small_sp", sp_model=True)
+        if name == "small_tr":   # "small" with 40 transparent (filler) words: exercises last_cword / -transp penalty
+            c = SynthConfig.preset("small")
+            return dataclasses.replace(c, name="small_tr", transparent_words=40)
         if name == "mono100":    # BASELINE config[0]: monophone 16-mix, 100 words
             return SynthConfig(name="mono100", seed=3, n_phones=40, n_states=120, n_mix=16,
                                phys_per_phone=1, vocab=100, n_bigrams=1500,
@@ -207,8 +211,9 @@ class SynthModel:
     def write_dict(self, path: str) -> None:
         with open(path, "w") as f:
             f.write(f"<s> [] {SIL}\n</s> [] {SIL}\n")
-            for w, pr in self.words:
-                f.write(f"{w} [{w}] " + " ".join(self.phones[p] for p in pr) + "\n")
+            for i, (w, pr) in enumerate(self.words):
+                out = f"{{{w}}}" if i < self.cfg.transparent_words else f"[{w}]"
+                f.write(f"{w} {out} " + " ".join(self.phones[p] for p in pr) + "\n")
 
     def write_arpa(self, path: str) -> None:
         with open(path, "w") as f:

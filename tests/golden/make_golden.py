@@ -33,6 +33,8 @@ CASES = {
     "small_mp": ("small", 2, 200, 1, ["-multipath", "-b", "120"]),
     # inter-word short pause (tee model => multipath by necessity), BASELINE configs[4] flavour
     "small_iwsp": ("small_sp", 2, 200, 1, ["-iwsp", "-iwcd1", "max", "-b", "150"]),
+    # 40 transparent (filler) words: last_cword differs from the last word, beam.c:2300-2330
+    "small_tr": ("small_tr", 2, 200, 1, ["-b", "100"]),
 }
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {

@@ -3,10 +3,10 @@ in tests/golden bit for bit -- this is what pins the oracle (prompt section 3)."
 import numpy as np
 import pytest
 
-from util import CASES, DNN_CASES, Golden, atoms_equal
+from util import CASES, DNN_CASES, ORACLE_ONLY_CASES, Golden, atoms_equal
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ORACLE_ONLY_CASES)
 def test_gmm_restatement_bit_exact(case, oracle_lib):
     g = Golden(case)
     for u, x in zip(g.utts, g.feats):
@@ -15,7 +15,7 @@ def test_gmm_restatement_bit_exact(case, oracle_lib):
         assert np.array_equal(sc.view(np.uint32), u.outprob.view(np.uint32))
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ORACLE_ONLY_CASES)
 def test_beam_restatement_identical_trellis(case, oracle_lib):
     g = Golden(case)
     for u in g.utts:
