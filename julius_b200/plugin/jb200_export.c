@@ -88,7 +88,18 @@ static int flatten_gmm(PROCESS_AM *am, jb200_blob *b) {
   HTK_HMM_State **byid;
 
   if (hi->opt.stream_info.num != 1) { jlog("ERROR: jb200: multi-stream AM is not supported\n"); return -1; }
-  if (hi->is_tied_mixture) { jlog("ERROR: jb200: tied-mixture AM is not supported yet\n"); return -1; }
+  if (hi->is_tied_mixture) {
+    /* Tied-mixture (codebook) states are flattened into ordinary states: the mixture list of a <TMIX> state is its
+     * codebook's densities with the state's own weights.  That IS what calc_tied_mix computes for -gprune none and
+     * safe (calc_tied_mix.c:161-248: codebook scores once per frame, + weight[id], addlog_array in list order;
+     * gprune_none lists ids in order, gprune_safe the N best sorted by score -- exactly what calc_mix does for a
+     * private mixture).  The true beam/heuristic pruning of codebooks seeds itself with the previous frame's best
+     * ids (calc_tied_mix.c:193-200), i.e. depends on which frames the search happened to evaluate: refused. */
+    if (am->config->gprune_method == GPRUNE_SEL_BEAM || am->config->gprune_method == GPRUNE_SEL_HEURISTIC) {
+      jlog("ERROR: jb200: tied-mixture AM with history-dependent Gaussian pruning; use -gprune none or -gprune safe\n");
+      return -1;
+    }
+  }
   if (!hi->variance_inversed) { jlog("ERROR: jb200: variances are expected to be inverted at this point\n"); return -1; }
   byid = (HTK_HMM_State **)calloc((size_t)S, sizeof(void *));
   for (st = hi->ststart; st; st = st->next) {
@@ -109,7 +120,7 @@ static int flatten_gmm(PROCESS_AM *am, jb200_blob *b) {
     if (!byid[i]) continue;
     p = byid[i]->pdf[0];
     for (m = 0; m < p->mix_num; m++) {
-      HTK_HMM_Dens *dn = p->b[m];
+      HTK_HMM_Dens *dn = p->tmix ? ((GCODEBOOK *)p->b)->d[m] : p->b[m];
       int g = off[i] + m;
       lnw[g] = p->bweight[m];
       if (dn == NULL) { valid[g] = 0; continue; }

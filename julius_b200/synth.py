@@ -46,6 +46,7 @@ class SynthConfig:
     one_phone_words: int = 0   # number of 1-phone words (exercise AS_LRSET)
     sp_model: bool = False     # add a 1-state tee model "sp" (skip transition) for -iwsp; forces multipath
     transparent_words: int = 0 # the first k words get a {..} output string: transparent to the LM context (fillers)
+    tied_mixture: bool = False # phonetic tied-mixture AM: one Gaussian codebook per (phone, state position), per-state weights
 
     @staticmethod
     def preset(name: str) -> "SynthConfig":
@@ -58,6 +59,9 @@ class SynthConfig:
         if name == "small_sp":   # "small" plus a short-pause tee model (-iwsp, multipath by necessity)
             c = SynthConfig.preset("small")
             return dataclasses.replace(c, name="small_sp", sp_model=True)
+        if name == "small_tm":   # phonetic tied-mixture variant of "small" (<TMIX> codebooks, calc_tied_mix.c)
+            c = SynthConfig.preset("small")
+            return dataclasses.replace(c, name="small_tm", tied_mixture=True, n_mix=16)
         if name == "small_tr":   # "small" with 40 transparent (filler) words: exercises last_cword / -transp penalty
             c = SynthConfig.preset("small")
             return dataclasses.replace(c, name="small_tr", transparent_words=40)
@@ -94,6 +98,18 @@ class SynthModel:
             for k in range(3):
                 if not part[c][k]:
                     part[c][k].append(int(order[(c * 3 + k) % S]))
+        # ---- tied mixture: the states of one (phone, position) cell share the cell's codebook (its first state's
+        #      Gaussians); the mixture weights stay per state
+        self.book_of = np.full(S, -1, dtype=np.int64)
+        if cfg.tied_mixture:
+            for c in range(P):
+                for k in range(3):
+                    first = part[c][k][0]
+                    for st_id in part[c][k]:
+                        self.book_of[st_id] = c * 3 + k
+                        self.mean[st_id] = self.mean[first]
+                        self.var[st_id] = self.var[first]
+            self.book_first = {c * 3 + k: part[c][k][0] for c in range(P) for k in range(3)}
         # ---- physical models: (state triple, transition macro)
         self.trans_names = ["T1", "T2", "T3"]
         self.trans_self = [0.6, 0.5, 0.7]
@@ -175,7 +191,20 @@ class SynthModel:
                 f.write(f'~t "{name}"\n<TRANSP> 5\n')
                 for row in a:
                     f.write(" " + " ".join(f"{x:.6e}" for x in row) + "\n")
-            for s in range(cfg.n_states):
+            if cfg.tied_mixture:
+                # codebook "cbNNN_": densities ~m "cbNNN_1" .. "cbNNN_M" (rdhmmdef_tiedmix.c:75-100 builds the index
+                # from name + number), states carry <TMIX> book weights (rdhmmdef_tiedmix.c:135-190)
+                for bk, first in sorted(self.book_first.items()):
+                    for m in range(M):
+                        f.write(f'~m "cb{bk:03d}_{m + 1}"\n')
+                        f.write(f"<MEAN> {D}\n " + " ".join(f"{x:.8e}" for x in self.mean[first, m]) + "\n")
+                        f.write(f"<VARIANCE> {D}\n " + " ".join(f"{x:.8e}" for x in self.var[first, m]) + "\n")
+                        g = D * ln2pi + float(np.sum(np.log(self.var[first, m].astype(np.float64))))
+                        f.write(f"<GCONST> {g:.8e}\n")
+                for s in range(cfg.n_states):
+                    f.write(f'~s "st{s}"\n<NUMMIXES> {M}\n<TMIX> cb{int(self.book_of[s]):03d}_ ')
+                    f.write(" ".join(f"{w:.8e}" for w in self.weight[s]) + "\n")
+            for s in range(cfg.n_states if not cfg.tied_mixture else 0):
                 f.write(f'~s "st{s}"\n<NUMMIXES> {M}\n')
                 for m in range(M):
                     f.write(f"<MIXTURE> {m + 1} {self.weight[s, m]:.8e}\n")

@@ -35,6 +35,8 @@ CASES = {
     "small_iwsp": ("small_sp", 2, 200, 1, ["-iwsp", "-iwcd1", "max", "-b", "150"]),
     # 40 transparent (filler) words: last_cword differs from the last word, beam.c:2300-2330
     "small_tr": ("small_tr", 2, 200, 1, ["-b", "100"]),
+    # phonetic tied-mixture AM (<TMIX> codebooks, calc_tied_mix.c), flattened by the exporter; safe pruning
+    "small_tm": ("small_tm", 2, 200, 1, ["-gprune", "safe", "-tmix", "4", "-b", "100"]),
 }
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {

@@ -21,7 +21,18 @@ SWEEP = [
     ("small_sp", ["-iwsp", "-b", "100", "-bs", "50", "-iwcd1", "avg"]),
     ("small", ["-gprune", "heuristic", "-tmix", "2", "-b", "90"]),
     ("small_tr", ["-multipath", "-b", "90"]),                    # transparent words on the multipath tree
+    ("small_tm", ["-gprune", "none", "-b", "100"]),              # tied-mixture codebooks, calc_tied_mix.c:161-248
+    ("small_tm", ["-gprune", "safe", "-tmix", "2", "-b", "80", "-multipath"]),
 ]
+
+
+@pytest.mark.skipif(not os.path.exists(JREF), reason="compiled reference (oracle/_ref/jref) not present")
+def test_tied_mixture_with_history_dependent_pruning_is_refused(tmp_path):
+    """-gprune beam (the default) on a tied-mixture AM seeds each codebook's pruning with the previous frame's best
+    ids, so its scores depend on which frames the search evaluated; the exporter must refuse rather than approximate."""
+    from oracle import fixtures
+    with pytest.raises(RuntimeError):
+        fixtures.make_fixture("small_tm", str(tmp_path), n_utts=1, n_frames=50, extra_args=["-b", "60"])
 
 
 @pytest.mark.skipif(not os.path.exists(JREF), reason="compiled reference (oracle/_ref/jref) not present")
