@@ -1,28 +1,119 @@
-// tools/heapsim.cpp -- CPU model of the pipelined heap-extraction schedule used by beam.cu
-// (heap_extract_pipelined) checked against the sequential loop of sort_token_upward (beam.c:1370-1384).
-// g++ -O2 -o heapsim tools/heapsim.cpp && ./heapsim 7     (argument: score divisor; small = many ties)
+// tools/heapsim.cpp -- CPU model of the beam cut as beam.cu runs it (heap_pad_sentinels + heap_extract_fast with the
+// loser cut), checked against the reference's loop (sort_token_upward / _downward, libjulius/src/beam.c:1342-1447).
+//
+//   g++ -O2 -o /tmp/heapsim tools/heapsim.cpp && /tmp/heapsim [score divisor, small = many exact ties] [trials]
+//
+// What is compared, per trial (n tokens, `need` survivors, random scores on a coarse grid so that ties are routine):
+//   upward selects   (need <  n-need): the order in which the `need` largest elements are extracted;
+//   downward selects (need >= n-need): the arrangement of the `need` elements left in the heap;
+//   and, without the cut, the complete final array (what the multipath kernel's select #1 needs).
+// The model mirrors the kernel statement by statement: freed tail slots and everything up to the last child slot hold
+// a sentinel, so the loop has no bounds tests; the address of the next children pair is clamped to a sentinel pair;
+// max-heap sifts stop when the larger child is below `lose_below` (a lower bound of the need-th largest score).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include <cstring>
-#include <algorithm>
-typedef unsigned long long u64;
-static float hval(u64 e){ unsigned b=(unsigned)(e&0xffffffffu); float f; memcpy(&f,&b,4); return f;}
-static bool hcmp(float a,float b){return a<b;} static bool hstop(float s,float c){return s>=c;}
-static void sift(std::vector<u64>&A,int start,int n){u64 s=A[start];float sv=hval(s);int p=start,c;while((c=p*2)<=n){u64 e=A[c];if(c<n&&hcmp(hval(A[c]),hval(A[c+1]))){c++;e=A[c];}if(hstop(sv,hval(e)))break;A[p]=e;p=c;}A[p]=s;}
-int main(int argc,char**argv){int n=2400,ext=800;int trials=2000;srand(1);long tick_tot=0;long bad_tot=0,haz_tot=0,badfin=0,badok=0;int mism=0;
- for(int tr=0;tr<trials;tr++){std::vector<u64>A(n+4);for(int i=1;i<=n;i++){float f=-(float)(rand()%20000)/ (float)(argc>1?atof(argv[1]):7.0f);unsigned b;memcpy(&b,&f,4);A[i]=((u64)(i-1)<<32)|b;}
-  for(int r=n/2;r>=1;r--)sift(A,r,n);
-  std::vector<u64>B=A; // sequential
-  {int m=n;while(m>n-ext){u64 s=B[m];B[m]=B[1];m--;if(m>=1){float sv=hval(s);int p=1,c;while((c=p*2)<=m){u64 e=B[c];if(c<m&&hcmp(hval(B[c]),hval(B[c+1]))){c++;e=B[c];}if(hstop(sv,hval(e)))break;B[p]=e;p=c;}B[p]=s;}}}
-  // pipelined
-  const int NL=16;struct L{bool act=false,has=false;int x=-1,par=1,m=0;u64 s=0;float sv=0,cl=0;};L ln[NL];std::vector<u64>outv(ext);int next_x=0,last=-2;bool bad=false;
-  for(int tick=0;;tick++){bool fin[NL];int pf[NL];for(int l=0;l<NL;l++){fin[l]=false;pf[l]=0;L&q=ln[l];if(q.act){int ch=q.par*2;if(ch>q.m){A[q.par]=q.s;fin[l]=true;pf[l]=q.par;}else{u64 c=A[ch];int cc=ch;if(ch<q.m&&hcmp(hval(A[ch]),hval(A[ch+1]))){cc=ch+1;c=A[ch+1];}if(hstop(q.sv,hval(c))){A[q.par]=q.s;fin[l]=true;pf[l]=q.par;}else{A[q.par]=c;q.par=cc;q.cl=hval(c);q.has=true;}}}}
-   for(int l=0;l<NL;l++)if(fin[l])ln[l].act=false;
-   if(next_x<ext&&tick-last>=2){int l=next_x%NL;int ms0=n-next_x;bool anc=false;for(int k=0;k<NL;k++)if(ln[k].act){int pp=ln[k].par;int a=ms0;while(a>pp)a>>=1;if(a==pp)anc=true;}if(!ln[l].act&&!anc){L&q=ln[l];int ms=n-next_x;q.s=A[ms];q.sv=hval(q.s);outv[next_x]=A[1];q.m=ms-1;q.x=next_x;q.par=1;q.has=false;q.act=(q.m>=1);next_x++;last=tick;}}
-   bool any=false;for(int l=0;l<NL;l++)any|=ln[l].act;if(bad)break;if(next_x>=ext&&!any){tick_tot+=tick;break;}}
-  if(bad){bad_tot++;continue;}
-  for(int x=0;x<ext;x++)if(outv[x]!=B[n-x]){mism++;break;}
-  for(int i=1;i<=n-ext;i++)if(A[i]!=B[i]){mism++;break;}
- }
- printf("ticks/extraction %.3f\n",(double)tick_tot/((double)trials*ext));printf("trials %d bad %ld (fin %ld ok %ld) hazards %ld mismatches %d\n",trials,bad_tot,badfin,badok,haz_tot,mism);}
+
+struct Ent { int id; float v; };
+static const float NEG = -INFINITY, POS = INFINITY;
+
+template <bool MAXHEAP> static bool hcmp(float a, float b) { return MAXHEAP ? (a < b) : (a > b); }      // "child < child+1"
+template <bool MAXHEAP> static bool hstop(float s, float c) { return MAXHEAP ? (s >= c) : (s <= c); }   // "STVAL >= SVAL(child)"
+
+template <bool MAXHEAP>
+static void sift_down(std::vector<Ent> &A, int start, int n) {          // the reference's inner loop, bounds tests and all
+  Ent s = A[start];
+  int parent = start, child;
+  while ((child = parent * 2) <= n) {
+    if (child < n && hcmp<MAXHEAP>(A[child].v, A[child + 1].v)) child++;
+    if (hstop<MAXHEAP>(s.v, A[child].v)) break;
+    A[parent] = A[child];
+    parent = child;
+  }
+  A[parent] = s;
+}
+
+// reference: build + extract in place; the k-th extracted root ends in slot n-k
+template <bool MAXHEAP>
+static void reference_select(std::vector<Ent> &A, int n, int extract) {
+  for (int root = n / 2; root >= 1; root--) sift_down<MAXHEAP>(A, root, n);
+  int m = n;
+  while (m > n - extract) {
+    Ent s = A[m];
+    A[m] = A[1];
+    m--;
+    if (m < 1) break;
+    A[1] = s;
+    sift_down<MAXHEAP>(A, 1, m);
+  }
+}
+
+// the kernel's formulation; outv[k] = k-th extracted root
+template <bool MAXHEAP>
+static void kernel_select(std::vector<Ent> &A, int n, int extract, int maxt, float lose_below, std::vector<Ent> &outv) {
+  const float sent = MAXHEAP ? NEG : POS;
+  for (int i = n + 1; i <= std::min(2 * n + 1, maxt + 1); i++) A[i] = Ent{0, sent};      // heap_pad_sentinels
+  A[maxt + 2] = A[maxt + 3] = Ent{0, sent};
+  for (int root = n / 2; root >= 1; root--) sift_down<MAXHEAP>(A, root, n);              // heap_build (level-parallel on the GPU)
+  const int cap = maxt / 2 + 1;                                                          // pair index of (maxt+2, maxt+3)
+  int mslot = n;
+  outv.assign(extract, Ent{-1, 0});
+  for (int x = 0; x < extract; x++) {
+    const Ent s = A[mslot];
+    A[mslot] = Ent{0, sent};                       // the slot leaves the heap
+    outv[x] = A[1];
+    mslot--;
+    int slot = 1, cur = 1;                         // parent slot, pair index of its children (slots 2*cur, 2*cur+1)
+    Ent x0 = A[2], y0 = A[3];
+    while (true) {
+      const bool right = hcmp<MAXHEAP>(x0.v, y0.v);
+      const int child = 2 * cur + (right ? 1 : 0);
+      const int ncur = std::min(child, cap);       // speculative load address (clamped)
+      const Ent nx = A[2 * ncur], ny = A[2 * ncur + 1];
+      const Ent c = right ? y0 : x0;
+      if (hstop<MAXHEAP>(s.v, c.v) || (MAXHEAP && c.v < lose_below)) break;
+      A[slot] = c;
+      slot = child;
+      cur = ncur;
+      x0 = nx; y0 = ny;
+    }
+    A[slot] = s;
+  }
+}
+
+int main(int argc, char **argv) {
+  const double divisor = argc > 1 ? atof(argv[1]) : 7.0;
+  const int trials = argc > 2 ? atoi(argv[2]) : 3000;
+  srand(1);
+  long mism = 0, checks = 0;
+  for (int tr = 0; tr < trials; tr++) {
+    const int n = 3 + rand() % 2600, need = 1 + rand() % (n - 1);
+    const int maxt = ((std::max(n, 64) + 63 + rand() % 500) + 3) & ~3;
+    std::vector<Ent> base(2 * maxt + 8, Ent{0, 0.0f});
+    std::vector<float> scores;
+    for (int i = 1; i <= n; i++) { base[i] = Ent{i - 1, -(float)(rand() % 20000) / (float)divisor}; scores.push_back(base[i].v); }
+    const bool upward = need < n - need;
+    const int extract = upward ? need : n - need;
+    std::vector<Ent> R = base, K = base, K2 = base, outv, outv2;
+    if (upward) {
+      std::sort(scores.begin(), scores.end(), std::greater<float>());
+      // any lower bound of the need-th largest score is legal; use one a little below it, as the histogram does
+      const float lose_below = scores[need - 1] - (float)(rand() % 3) * 0.5f;
+      reference_select<true>(R, n, extract);
+      kernel_select<true>(K, n, extract, maxt, lose_below, outv);
+      kernel_select<true>(K2, n, extract, maxt, NEG, outv2);           // no cut: the whole array must agree
+      for (int k = 0; k < extract; k++) { checks++; if (outv[k].id != R[n - k].id) { mism++; break; } }
+      for (int k = 0; k < extract; k++) K2[n - k] = outv2[k];
+      for (int i = 1; i <= n; i++) { checks++; if (K2[i].id != R[i].id) { mism++; break; } }
+    } else {
+      reference_select<false>(R, n, extract);
+      kernel_select<false>(K, n, extract, maxt, NEG, outv);
+      for (int i = 1; i <= need; i++) { checks++; if (K[i].id != R[i].id) { mism++; break; } }
+      for (int k = 0; k < extract; k++) { checks++; if (outv[k].id != R[n - k].id) { mism++; break; } }
+    }
+  }
+  printf("trials %d, element checks %ld, mismatches %ld\n", trials, checks, mism);
+  return mism != 0;
+}
