@@ -144,7 +144,20 @@ typedef struct {
   const int32_t *bi_num;     /* [lm_nvocab] */
   const int32_t *bi_wid;     /* [lm_nbigram] nnid2wid */
   const float *bi_prob;      /* [lm_nbigram] d[1].prob (or p_2) */
+  /* ---- grammar (DFA) mode, category tree (beam.c:1669-1760, :2404-2455, :435-458).  lm_type = JB200_LM_DFA:
+   * every root is listed in iso_* (n_shared = 0, no factoring: scid is all zero), the bigram arrays are empty, and
+   * a cross-word transition from word w into root i is allowed iff cp_allowed[w * n_iso + iso_id[i]] (the category
+   * pair constraint dfa_cp(category(w), category(start2wid))); its language score is penalty1 + cprob[w]. */
+  int32_t lm_type;           /* JB200_LM_NGRAM / JB200_LM_DFA */
+  int32_t n_init;            /* sentence-initial words (dfa_cp_begin), in the order init_nodescore creates their tokens */
+  float penalty1;            /* -penalty1: word insertion penalty of pass 1 */
+  int32_t reserved_;
+  const int32_t *init_word;  /* [n_init] */
+  const int32_t *init_node;  /* [n_init] offset[w][0], or wordbegin[w] on a multipath tree */
+  const float *init_lscore;  /* [n_init] penalty1 + cprob[w] */
+  const uint8_t *cp_allowed; /* [n_words][n_iso] */
 } jb200_tree_desc;
+enum { JB200_LM_NGRAM = 0, JB200_LM_DFA = 1 };
 
 /* ======================================================================================
  * "JB2M" blob container: a flat list of named little-endian arrays.
@@ -327,6 +340,8 @@ static inline int jb200_tree_from_blob(const jb200_blob *b, jb200_tree_desc *t) 
   JB200_GP(fscore, float); JB200_GP(scword, int32_t);
   JB200_GP(uni_prob, float); JB200_GP(uni_bow, float); JB200_GP(bi_bgn, int32_t); JB200_GP(bi_num, int32_t);
   JB200_GP(bi_wid, int32_t); JB200_GP(bi_prob, float);
+  JB200_GI(lm_type); JB200_GI(n_init); JB200_GF(penalty1);
+  JB200_GP(init_word, int32_t); JB200_GP(init_node, int32_t); JB200_GP(init_lscore, float); JB200_GP(cp_allowed, uint8_t);
 #undef JB200_GI
 #undef JB200_GF
 #undef JB200_GP

@@ -1651,6 +1651,7 @@ extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
 
 extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int max_utts, int max_frames, jb200_decoder **out) {
   if (!t || !am || !out || max_utts < 1 || max_frames < 1) { set_error("jb200_decoder_create: bad argument"); return JB200_ERR_ARG; }
+  if (t->lm_type != JB200_LM_NGRAM) { set_error("grammar (DFA) lexicon trees are not supported by the GPU beam yet (lm_type %d)", t->lm_type); return JB200_ERR_UNSUPPORTED; }
   if (t->n_nodes >= (1 << 28)) { set_error("lexicon tree too large"); return JB200_ERR_UNSUPPORTED; }
   if (t->beam_width < 1 || t->beam_width > 8000) { set_error("beam width %d outside 1..8000", t->beam_width); return JB200_ERR_UNSUPPORTED; }
   jb200_decoder *d = new jb200_decoder();

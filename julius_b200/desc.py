@@ -44,9 +44,15 @@ _TREE_PTRS = (("self_a", F), ("next_a", F), ("arc_off", I), ("arc_to", I), ("arc
               ("bi_bgn", I), ("bi_num", I), ("bi_wid", I), ("bi_prob", F))
 
 
+# grammar (DFA) mode tail of jb200_tree_desc (absent from blobs of N-gram models)
+_TREE_DFA_PTRS = (("init_word", I), ("init_node", I), ("init_lscore", F), ("cp_allowed", U8))
+
+
 class TreeDesc(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _TREE_INTS] + [(n, C.c_float) for n in _TREE_FLOATS]
-                + list(_TREE_PTRS))
+                + list(_TREE_PTRS)
+                + [("lm_type", C.c_int32), ("n_init", C.c_int32), ("penalty1", C.c_float), ("reserved_", C.c_int32)]
+                + list(_TREE_DFA_PTRS))
 
 
 def _ptr(keep: list, a: np.ndarray, ctype):
@@ -108,6 +114,11 @@ class Descriptors:
             setattr(t, n, float(_sc(b, "tree." + n, -1.0 if n == "score_pruning_width" else 0.0)))
         for n, ct in _TREE_PTRS:
             setattr(t, n, _ptr(k, b["tree." + n], ct))
+        t.lm_type = int(_sc(b, "tree.lm_type", 0)); t.n_init = int(_sc(b, "tree.n_init", 0))
+        t.penalty1 = float(_sc(b, "tree.penalty1", 0.0))
+        np_of = {I: np.int32, F: np.float32, U8: np.uint8}
+        for n, ct in _TREE_DFA_PTRS:
+            setattr(t, n, _ptr(k, b.get("tree." + n, np.zeros(1, np_of[ct])), ct))
         return t
 
     def cd_only_gmm(self) -> GmmDesc:

@@ -193,18 +193,25 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
   float *arc_a;
   unsigned char *outstyle;
   /* context classes */
-  typedef struct { HMM_Logical *hmm; int loc; int style; } RKey;
+  typedef struct { HMM_Logical *hmm; int loc; int style; int cat; } RKey;
   RKey *rkeys = NULL; int nr = 0, rcap = 0;
   char **ctxnames; int nctx = 0;
   int *word_ctx;
   char buf[MAX_HMMNAME_LEN], rbuf[MAX_HMMNAME_LEN];
 
-  if (w->lmtype != LM_PROB || ng == NULL) {
-    jlog("ERROR: jb200: only N-gram (LM_PROB) lexicon trees are supported by the GPU beam\n");
-    return -1;
+  const int is_dfa = (w->lmtype == LM_DFA);
+  if (is_dfa) {
+    /* grammar mode: category tree + category-pair constraint only (beam.c:2404-2455) */
+    if (w->lmvar != LM_DFA_GRAMMAR || !w->category_tree || w->dfa == NULL) {
+      jlog("ERROR: jb200: grammar mode needs a category tree over a DFA grammar (isolated-word mode is not supported)\n");
+      return -1;
+    }
+    if (w->dfa_forward != NULL) { jlog("ERROR: jb200: forward-DFA state tracking (.dfa.forward) is not supported\n"); return -1; }
+  } else {
+    if (w->lmtype != LM_PROB || ng == NULL) { jlog("ERROR: jb200: lexicon tree without a language model\n"); return -1; }
+    if (w->category_tree) { jlog("ERROR: jb200: category tree with an N-gram is not supported\n"); return -1; }
+    if (w->lmvar == LM_NGRAM_USER) { jlog("ERROR: jb200: user-defined LM functions are not supported\n"); return -1; }
   }
-  if (w->category_tree) { jlog("ERROR: jb200: category tree (grammar) mode is not supported\n"); return -1; }
-  if (w->lmvar == LM_NGRAM_USER) { jlog("ERROR: jb200: user-defined LM functions are not supported\n"); return -1; }
 
   /* ---- arcs (A_CELL2 lists, kept in the order beam_intra_word walks them, beam.c:2172-2176) */
   arc_off = (int *)malloc(sizeof(int) * (n + 1));
@@ -239,20 +246,23 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
   outstyle = (unsigned char *)malloc((size_t)n);
   for (i = 0; i < n; i++) {
     stend[i] = (w->stend[i] == WORD_INVALID) ? -1 : (int)w->stend[i];
-    scid[i] = w->state[i].scid;
+    scid[i] = is_dfa ? 0 : w->state[i].scid;      /* no factoring inside a category tree (beam.c:2028) */
     if (w->state[i].out.state == NULL) { outstyle[i] = 255; out_ref[i] = -1; continue; }
     switch (w->outstyle[i]) {
       case AS_STATE: outstyle[i] = JB200_AS_STATE; out_ref[i] = w->state[i].out.state->id; break;
       case AS_LSET:  outstyle[i] = JB200_AS_LSET;  out_ref[i] = cd_intern(cd, w->state[i].out.lset); break;
       case AS_RSET:
       case AS_LRSET: {
-        HMM_Logical *h; int loc, style, j, found = -1;
+        HMM_Logical *h; int loc, style, j, found = -1, cat = -1;
         if (w->outstyle[i] == AS_RSET) { h = w->state[i].out.rset->hmm; loc = w->state[i].out.rset->state_loc; style = JB200_AS_RSET; }
-        else { h = w->state[i].out.lrset->hmm; loc = w->state[i].out.lrset->state_loc; style = JB200_AS_LRSET; }
-        for (j = 0; j < nr; j++) if (rkeys[j].hmm == h && rkeys[j].loc == loc && rkeys[j].style == style) { found = j; break; }
+        else {
+          h = w->state[i].out.lrset->hmm; loc = w->state[i].out.lrset->state_loc; style = JB200_AS_LRSET;
+          if (w->category_tree) cat = (int)w->state[i].out.lrset->category;     /* category-indexed cd sets, outprob_style.c:448-459 */
+        }
+        for (j = 0; j < nr; j++) if (rkeys[j].hmm == h && rkeys[j].loc == loc && rkeys[j].style == style && rkeys[j].cat == cat) { found = j; break; }
         if (found < 0) {
           if (nr == rcap) { rcap = rcap ? rcap * 2 : 256; rkeys = (RKey *)realloc(rkeys, sizeof(RKey) * rcap); }
-          rkeys[nr].hmm = h; rkeys[nr].loc = loc; rkeys[nr].style = style; found = nr++;
+          rkeys[nr].hmm = h; rkeys[nr].loc = loc; rkeys[nr].style = style; rkeys[nr].cat = cat; found = nr++;
         }
         outstyle[i] = (unsigned char)style; out_ref[i] = found;
       } break;
@@ -275,12 +285,18 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
           if (rhmm->is_pseudo) ref = -cd_intern(cd, &(rhmm->body.pseudo->stateset[loc])) - 1;
           else ref = rhmm->body.defined->s[loc]->id;
         } else {
-          /* outprob_style.c:437-486, N-gram branch (no category tree) */
+          /* outprob_style.c:437-486 */
           CD_Set *lcd;
           rhmm = base;
           strcpy(rbuf, rhmm->name);
           if (c < nctx) add_left_context(rbuf, ctxnames[c]);
-          lcd = lcdset_lookup_by_hmmname(hi, rbuf);
+          if (w->category_tree) {
+            /* category-indexed cd sets (outprob_style.c:448-459) */
+            if (c < nctx && (ohmm = get_left_context_HMM(rhmm, ctxnames[c], hi)) != NULL)
+              lcd = lcdset_lookup_with_category(w, ohmm, (WORD_ID)rkeys[i].cat);
+            else
+              lcd = lcdset_lookup_with_category(w, rhmm, (WORD_ID)rkeys[i].cat);
+          } else lcd = lcdset_lookup_by_hmmname(hi, rbuf);
           if (lcd != NULL) ref = -cd_intern(cd, &(lcd->stateset[loc])) - 1;
           else if (rhmm->is_pseudo) ref = -cd_intern(cd, &(rhmm->body.pseudo->stateset[loc])) - 1;
           else ref = rhmm->body.defined->s[loc]->id;
@@ -298,12 +314,18 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
     int stid;
     for (stid = w->startnum - 1; stid >= 0; stid--) {
       int node = w->startnode[stid];
-      int iso = w->start2isolate[stid];
+      int iso;
+      if (is_dfa) {
+        /* grammar mode: every root takes cross-word arrivals, gated by the category pair (beam.c:2404-2411) */
+        iv_push(&iso_node, node); iv_push(&iso_id, stid); iv_push(&iso_word, (int)w->start2wid[stid]);
+        continue;
+      }
+      iso = w->start2isolate[stid];
       if (iso == -1) { iv_push(&shared, node); continue; }
       if (w->state[node].scid <= 0) { jlog("ERROR: jb200: isolated root without successor word\n"); return -1; }
       iv_push(&iso_node, node); iv_push(&iso_id, iso); iv_push(&iso_word, (int)w->scword[w->state[node].scid]);
     }
-    if (iso_node.n != w->isolatenum) { jlog("ERROR: jb200: isolatenum mismatch\n"); return -1; }
+    if (!is_dfa && iso_node.n != w->isolatenum) { jlog("ERROR: jb200: isolatenum mismatch\n"); return -1; }
     jb200_blob_add_i(b, "tree.n_iso", iso_node.n);
     jb200_blob_add_i(b, "tree.n_shared", shared.n);
     jb200_blob_add(b, "tree.iso_node", JB200_I32, iso_node.n, iso_node.d ? iso_node.d : (int *)&stid);
@@ -337,6 +359,59 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
     free(wea); free(cprob); free(wend); free(wbeg); free(wton); free(tr);
   }
 
+  if (is_dfa) {
+    /* ---- grammar mode: category-pair table, sentence-initial words, penalty (beam.c:1669-1760, :2444-2450) */
+    DFA_INFO *dfa = w->dfa;
+    const int ns = w->startnum;
+    unsigned char *cp = (unsigned char *)calloc((size_t)V * (ns ? ns : 1), 1);
+    IVec iw_ = {0}, in_ = {0};
+    float *il;
+    MULTIGRAM *m;
+    float zero = 0.0f; int izero = 0;
+    for (i = 0; i < V; i++)
+      for (k = 0; k < ns; k++)
+        cp[(size_t)i * ns + k] = dfa_cp(dfa, (int)wi->wton[i], (int)wi->wton[w->start2wid[k]]) ? 1 : 0;
+    for (m = r->lm->grammars; m; m = m->next) {
+      int t, tb, te;
+      if (!m->active) continue;
+      tb = m->cate_begin; te = tb + m->dfa->term_num;
+      for (t = tb; t < te; t++) {
+        int x;
+        if (!dfa_cp_begin(dfa, t)) continue;
+        for (x = 0; x < dfa->term.wnum[t]; x++) {
+          int wd = (int)dfa->term.tw[t][x], node = hi->multipath ? w->wordbegin[wd] : w->offset[wd][0], dup = 0, y;
+          for (y = 0; y < in_.n; y++) if (in_.d[y] == node) { dup = 1; break; }     /* node_exist_token, beam.c:1719 */
+          if (dup) continue;
+          iv_push(&iw_, wd); iv_push(&in_, node);
+        }
+      }
+    }
+    il = (float *)calloc((size_t)(iw_.n ? iw_.n : 1), sizeof(float));
+    for (i = 0; i < iw_.n; i++) {
+      float ls = r->config->lmp.penalty1;
+#ifdef CLASS_NGRAM
+      ls += wi->cprob[iw_.d[i]];
+#endif
+      il[i] = ls;
+    }
+    jb200_blob_add_i(b, "tree.lm_type", JB200_LM_DFA);
+    jb200_blob_add_i(b, "tree.n_init", iw_.n);
+    jb200_blob_add_f(b, "tree.penalty1", r->config->lmp.penalty1);
+    jb200_blob_add(b, "tree.init_word", JB200_I32, iw_.n, iw_.d ? iw_.d : &izero);
+    jb200_blob_add(b, "tree.init_node", JB200_I32, in_.n, in_.d ? in_.d : &izero);
+    jb200_blob_add(b, "tree.init_lscore", JB200_F32, iw_.n, il);
+    jb200_blob_add(b, "tree.cp_allowed", JB200_U8, (int64_t)V * ns, cp);
+    /* the N-gram side of the descriptor stays empty */
+    jb200_blob_add_i(b, "tree.n_fscore", 0); jb200_blob_add_i(b, "tree.n_scword", 0);
+    jb200_blob_add(b, "tree.fscore", JB200_F32, 0, &zero); jb200_blob_add(b, "tree.scword", JB200_I32, 0, &izero);
+    jb200_blob_add_i(b, "tree.lm_nvocab", 0); jb200_blob_add_i(b, "tree.lm_nbigram", 0);
+    jb200_blob_add_i(b, "tree.lm_mode", 0); jb200_blob_add_i(b, "tree.lm_unk_id", -1);
+    jb200_blob_add_f(b, "tree.lm_unk_num_log", 0.0f);
+    jb200_blob_add(b, "tree.uni_prob", JB200_F32, 0, &zero); jb200_blob_add(b, "tree.uni_bow", JB200_F32, 0, &zero);
+    jb200_blob_add(b, "tree.bi_bgn", JB200_I32, 0, &izero); jb200_blob_add(b, "tree.bi_num", JB200_I32, 0, &izero);
+    jb200_blob_add(b, "tree.bi_wid", JB200_I32, 0, &izero); jb200_blob_add(b, "tree.bi_prob", JB200_F32, 0, &zero);
+    free(cp); free(iw_.d); free(in_.d); free(il);
+  } else {
   /* ---- factoring values */
   {
     int *scw = (int *)calloc((size_t)w->scnum + 1, sizeof(int));
@@ -378,6 +453,7 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
     jb200_blob_add(b, "tree.bi_prob", JB200_F32, (int64_t)t2->totalnum, biprob);
     free(bgn); free(num); free(bwid);
   }
+  }
 
   /* ---- scalars + per-node arrays */
   jb200_blob_add_i(b, "tree.n_nodes", n);
@@ -386,8 +462,8 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
   jb200_blob_add_i(b, "tree.n_start", w->startnum);
   jb200_blob_add_i(b, "tree.n_rset", nr);
   jb200_blob_add_i(b, "tree.n_ctx", nctx);
-  jb200_blob_add_i(b, "tree.head_silwid", (int)wi->head_silwid);
-  jb200_blob_add_i(b, "tree.tail_silwid", (int)wi->tail_silwid);
+  jb200_blob_add_i(b, "tree.head_silwid", (is_dfa || wi->head_silwid == WORD_INVALID) ? -1 : (int)wi->head_silwid);
+  jb200_blob_add_i(b, "tree.tail_silwid", (is_dfa || wi->tail_silwid == WORD_INVALID) ? -1 : (int)wi->tail_silwid);
   jb200_blob_add_i(b, "tree.multipath", hi->multipath ? 1 : 0);
   jb200_blob_add_i(b, "tree.beam_width", r->trellis_beam_width);
   jb200_blob_add_f(b, "tree.lm_weight", r->config->lmp.lm_weight);

@@ -255,6 +255,48 @@ class SynthModel:
                 f.write(f"{lp:.6f} {self.lm_vocab[a]} {self.lm_vocab[b]}\n")
             f.write("\n\\end\\\n")
 
+    # ------------------------------------------------------------------ grammar (DFA) mode
+    GRAMMAR_NEXT = {0: (2, 3), 2: (3, 4), 3: (4, 5), 4: (5, 2, 1), 5: (2, 1)}    # category -> categories that may follow
+
+    def write_grammar(self, outdir: str, prefix: str = "g") -> dict:
+        """A finite-state grammar over the same vocabulary in the reference's formats (-dfa/-v, or -gram prefix):
+        category 0 = sentence-initial silence, 1 = sentence-final silence, words spread over categories 2..5;
+        GRAMMAR_NEXT is the forward category-pair relation.  The .dfa file is the REVERSED automaton Julius expects
+        (rddfa.c:125-200: `state category next_state accept-flag`, state 0 initial, it reads the sentence from its
+        last word), the .dict file carries the category id in the first column."""
+        os.makedirs(outdir, exist_ok=True)
+        cats = sorted(set(self.GRAMMAR_NEXT) | {c for v in self.GRAMMAR_NEXT.values() for c in v})
+        state_of = {c: i + 1 for i, c in enumerate(c for c in cats if c != 0)}     # "the category to the right is c"
+        final = len(state_of) + 1
+        lines = [f"0 1 {state_of[1]} 0 0"]
+        for p_cat, nxt in sorted(self.GRAMMAR_NEXT.items()):
+            for c in nxt:
+                if p_cat == 0:
+                    lines.append(f"{state_of[c]} 0 {final} 0 0")
+                else:
+                    lines.append(f"{state_of[c]} {p_cat} {state_of[p_cat]} 0 0")
+        lines.append(f"{final} -1 -1 1 0")
+        dfa = os.path.join(outdir, prefix + ".dfa")
+        with open(dfa, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        dic = os.path.join(outdir, prefix + ".dict")
+        with open(dic, "w") as f:
+            f.write(f"0 [<s>] {SIL}\n1 [</s>] {SIL}\n")
+            for i, (w, pr) in enumerate(self.words):
+                f.write(f"{2 + i % 4} [{w}] " + " ".join(self.phones[p] for p in pr) + "\n")
+        return {"dfa": dfa, "dict": dic}
+
+    def sample_grammar_sentence(self, rng: np.random.Generator, n_words: int):
+        """word indices of a sentence the grammar accepts (without the silences)"""
+        by_cat = {c: [i for i in range(len(self.words)) if 2 + i % 4 == c] for c in (2, 3, 4, 5)}
+        out, cat = [], 0
+        while True:
+            nxt = [c for c in self.GRAMMAR_NEXT[cat] if c != 1]
+            if len(out) >= n_words and 1 in self.GRAMMAR_NEXT[cat]:
+                return out
+            cat = int(rng.choice(nxt))
+            out.append(int(rng.choice(by_cat[cat])))
+
     def write_all(self, outdir: str) -> dict:
         os.makedirs(outdir, exist_ok=True)
         paths = {k: os.path.join(outdir, k) for k in ("hmmdefs", "hmmlist", "dict", "lm.arpa")}
@@ -265,7 +307,7 @@ class SynthModel:
         return paths
 
     # ------------------------------------------------------------------ features
-    def sample_utterance(self, rng: np.random.Generator, n_frames: int, noise: float = 1.0):
+    def sample_utterance(self, rng: np.random.Generator, n_frames: int, noise: float = 1.0, word_seq=None):
         """Sample ~n_frames feature frames along a random ``<s> w.. </s>`` path.
 
         Returns (feats [T, D] float32, word index list).  T is exactly n_frames:
@@ -287,7 +329,11 @@ class SynthModel:
 
         # <s>
         seq = [[0]]
-        while True:
+        if word_seq is not None:             # a given word sequence (e.g. a sentence of the grammar)
+            for wi in word_seq:
+                seq.append(self.words[wi][1])
+                words.append(int(wi))
+        while word_seq is None:
             wi = int(rng.integers(len(self.words)))
             seq.append(self.words[wi][1])
             words.append(wi)

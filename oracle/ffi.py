@@ -108,11 +108,12 @@ def have_ref() -> bool:
 def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "out.jrf", export: str | None = None,
             tokens: bool = False, am_args: list | None = None, quiet: bool = True, timeout: int = 3600,
             binary: str | None = None, env_extra: dict | None = None, two_pass: bool = False,
-            outprobout: bool = True):
+            outprobout: bool = True, lm_args: list | None = None):
     """Run the compiled reference on HTK parameter files; returns (dump path, stdout).
     two_pass: also run the stack-decoding pass 2 and print its sentences (JREF_RESULT lines).
     outprobout: pass "-outprobout /dev/null", which makes the host evaluate the complete [T x S] score
-    matrix (what the dump's outprob section needs); it requires a populated score cache."""
+    matrix (what the dump's outprob section needs); it requires a populated score cache.
+    lm_args: language-model options instead of the N-gram default, e.g. ["-dfa", "g.dfa", "-v", "g.dict"]."""
     env = dict(os.environ)
     if quiet:
         env["JREF_QUIET"] = "1"
@@ -126,7 +127,7 @@ def run_ref(workdir: str, filelist: list, extra_args: list = (), dump: str = "ou
         env.update(env_extra)
     args = [binary or JREF, "-dump", os.path.join(workdir, dump), "-plugindir", PLUGDIR]
     args += am_args if am_args is not None else ["-h", "hmmdefs", "-hlist", "hmmlist"]
-    args += ["-v", "dict", "-nlr", "lm.arpa", "-input", "mfcfile"] + ([] if two_pass else ["-1pass"]) + (["-outprobout", "/dev/null"] if outprobout else [])
+    args += (lm_args if lm_args is not None else ["-v", "dict", "-nlr", "lm.arpa"]) + ["-input", "mfcfile"] + ([] if two_pass else ["-1pass"]) + (["-outprobout", "/dev/null"] if outprobout else [])
     args += list(extra_args)
     p = subprocess.run(args, input="\n".join(filelist) + "\n", text=True, cwd=workdir, env=env,
                        capture_output=True, timeout=timeout)

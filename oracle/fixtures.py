@@ -18,15 +18,22 @@ from . import ffi
 
 
 def make_fixture(preset, outdir: str, n_utts: int = 2, n_frames: int = 200, seed: int = 11,
-                 extra_args: list = (), tokens: bool = False, noise_utts: int = 0, model=None):
+                 extra_args: list = (), tokens: bool = False, noise_utts: int = 0, model=None, grammar: bool = False):
+    """grammar=True: decode with the synthetic finite-state grammar (-dfa/-v) instead of the N-gram; the sampled
+    utterances then follow sentences of that grammar."""
     cfg = synth.SynthConfig.preset(preset) if isinstance(preset, str) else preset
     m = model if model is not None else synth.SynthModel(cfg)
     if model is None or not os.path.exists(os.path.join(outdir, "hmmdefs")):
         m.write_all(outdir)
     rng = np.random.default_rng(seed)
     files = []
+    lm_args = None
+    if grammar:
+        g = m.write_grammar(outdir)
+        lm_args = ["-dfa", os.path.basename(g["dfa"]), "-v", os.path.basename(g["dict"])]
     for u in range(n_utts):
-        x, _ = m.sample_utterance(rng, n_frames)
+        ws = m.sample_grammar_sentence(rng, max(2, n_frames // 45)) if grammar else None
+        x, _ = m.sample_utterance(rng, n_frames, word_seq=ws)
         fn = os.path.join(outdir, f"u{u}.mfc")
         synth.write_htk_param(fn, x)
         files.append(fn)
@@ -37,5 +44,5 @@ def make_fixture(preset, outdir: str, n_utts: int = 2, n_frames: int = 200, seed
     with open(os.path.join(outdir, "list.txt"), "w") as f:
         f.write("\n".join(files) + "\n")
     dump, out = ffi.run_ref(outdir, files, extra_args=extra_args, export=os.path.join(outdir, "model.jb2m"),
-                            tokens=tokens)
+                            tokens=tokens, lm_args=lm_args)
     return m, files, dump, out

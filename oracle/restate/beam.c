@@ -283,12 +283,34 @@ static void propagate_from_root(Beam *b, int root, float tmpsum, int tre, int la
   for (k = t->arc_off[root]; k < t->arc_off[root + 1]; k++) propagate_token(b, t->arc_to[k], tmpsum + t->arc_a[k], tre, last_word, lsc);
 }
 
+/* grammar mode: every root, gated by the category pair of (ending word, root's word); the language score is the
+ * insertion penalty (beam.c:2404-2411, :2444-2450; CLASS_NGRAM adds cprob[last_word]) */
+static void beam_inter_word_dfa(Beam *b, const Tok *tk, int tre) {
+  const jb200_tree_desc *t = b->t;
+  int node = tk->node, sword = t->stend[node], i, last_word;
+  float tmpsum, ngram_score_cache;
+  last_word = t->is_transparent[sword] ? tk->last_cword : sword;
+  for (i = 0; i < t->n_iso; i++) {
+    int next_node = t->iso_node[i];
+    if (!t->cp_allowed[(size_t)sword * t->n_iso + t->iso_id[i]]) continue;
+    tmpsum = tk->score;
+    if (!t->multipath) tmpsum += t->wordend_a[sword];
+    ngram_score_cache = t->penalty1;
+    ngram_score_cache += t->cprob[last_word];
+    tmpsum += ngram_score_cache;
+    if (t->multipath) propagate_from_root(b, next_node, tmpsum, tre, last_word, ngram_score_cache);
+    else propagate_token(b, next_node, tmpsum, tre, last_word, ngram_score_cache);
+  }
+}
+
 static void beam_inter_word(Beam *b, const Tok *tk, int tre) {
   const jb200_tree_desc *t = b->t;
   int node = tk->node, sword = t->stend[node], i, last_word;
   float tmpprob, tmpsum, ngram_score_cache;
   const float *iwparray;
-  int transp_s = t->is_transparent[sword];
+  int transp_s;
+  if (t->lm_type == JB200_LM_DFA) { beam_inter_word_dfa(b, tk, tre); return; }
+  transp_s = t->is_transparent[sword];
   last_word = transp_s ? tk->last_cword : sword;
   if (sword == t->tail_silwid) return;
   tmpprob = tk->score;
@@ -337,6 +359,24 @@ static void init_frame0(Beam *b) {
   int node, newid; Tok *nw;
   b->tn = 0; b->tl = 1;
   b->tnum[0] = b->tnum[1] = 0;
+  if (t->lm_type == JB200_LM_DFA) {
+    /* init_nodescore, grammar branch (beam.c:1669-1760): one token per sentence-initial word (duplicates of a
+     * shared first node were dropped when the list was made), in the reference's creation order */
+    int i;
+    for (i = 0; i < t->n_init; i++) {
+      node = t->init_node[i];
+      newid = create_token(b);
+      nw = &b->tlist[b->tn][newid];
+      nw->last_tre = -1; nw->last_cword = -1;       /* the bos atom: wid = WORD_INVALID */
+      nw->last_lscore = t->init_lscore[i];
+      if (t->multipath) nw->score = nw->last_lscore;
+      else nw->score = outprob_style(b, node, -1, 0) + nw->last_lscore;
+      b->token[node] = newid; nw->node = node;
+    }
+    sort_token_no_order(b, t->beam_width, &b->n_start, &b->n_end);
+    b->score_pruning_threshold = JB200_LOG_ZERO;
+    return;
+  }
   newid = create_token(b);
   nw = &b->tlist[b->tn][newid];
   node = t->wordbegin[t->head_silwid];      /* offset[beginword][0] */
@@ -501,6 +541,11 @@ int oracle_beam_decode(const jb200_tree_desc *t, const jb200_gmm_desc *g,
       float maxscore = JB200_LOG_ZERO;
       for (i = 0; i < nkeep; i++) {
         if (atoms_out[i].endtime != last_time) continue;
+        if (t->lm_type == JB200_LM_DFA) {
+          /* grammar mode (beam.c:435-458): the best atom of the last frame that holds any */
+          if (maxscore < atoms_out[i].backscore) { maxscore = atoms_out[i].backscore; found = i; }
+          continue;
+        }
         if (atoms_out[i].wid == t->tail_silwid && maxscore < atoms_out[i].backscore) { maxscore = atoms_out[i].backscore; found = i; break; }
       }
     }

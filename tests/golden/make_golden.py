@@ -24,6 +24,9 @@ from oracle import ffi, fixtures  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
+# grammar (DFA) mode cases: the LM is the synthetic finite-state grammar of julius_b200.synth.write_grammar
+GRAMMAR_CASES = {"small_dfa"}
+
 CASES = {
     # name: (preset, n_utts, n_frames, noise_utts, extra args)
     "tiny": ("tiny", 2, 150, 0, []),
@@ -37,6 +40,8 @@ CASES = {
     "small_tr": ("small_tr", 2, 200, 1, ["-b", "100"]),
     # phonetic tied-mixture AM (<TMIX> codebooks, calc_tied_mix.c), flattened by the exporter; safe pruning
     "small_tm": ("small_tm", 2, 200, 1, ["-gprune", "safe", "-tmix", "4", "-b", "100"]),
+    # grammar mode (category tree + category-pair constraint, beam.c:1669-1760, :2404-2455), BASELINE configs[0] flavour
+    "small_dfa": ("small", 2, 200, 1, ["-b", "80", "-penalty1", "-1.0"]),
 }
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {
@@ -54,7 +59,8 @@ def main():
         if only and name not in only:
             continue
         tmp = tempfile.mkdtemp(prefix="jb200_golden_")
-        m, files, dump, out = fixtures.make_fixture(preset, tmp, n_utts=nu, n_frames=nf, noise_utts=nn, extra_args=extra)
+        m, files, dump, out = fixtures.make_fixture(preset, tmp, n_utts=nu, n_frames=nf, noise_utts=nn, extra_args=extra,
+                                                    grammar=name in GRAMMAR_CASES)
         dst = os.path.join(HERE, name)
         os.makedirs(dst, exist_ok=True)
         shutil.copy(os.path.join(tmp, "model.jb2m"), dst)
@@ -62,7 +68,8 @@ def main():
         feats = {f"u{i}": synth.read_htk_param(fn)[0] for i, fn in enumerate(files)}
         np.savez_compressed(os.path.join(dst, "feats.npz"), **feats)
         with open(os.path.join(dst, "meta.json"), "w") as f:
-            json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "summary": out.strip().splitlines()[-1]}, f, indent=1)
+            json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "grammar": name in GRAMMAR_CASES,
+                       "summary": out.strip().splitlines()[-1]}, f, indent=1)
         shutil.rmtree(tmp)
         print(name, "->", dst)
     for name, (preset, dkw, nu, nf, extra) in DNN_CASES.items():

@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from julius_b200 import capi, desc, refdump, synth
 from util import GOLDEN, ROOT, Golden
@@ -49,3 +50,36 @@ def test_synth_is_seeded(tmp_path):
     synth.write_htk_param(str(p), x)
     y, kind = synth.read_htk_param(str(p))
     assert np.array_equal(x, y) and kind == synth.PARMKIND_MFCC_E_D_A
+
+
+def test_descriptor_layouts_match_the_c_header(tmp_path):
+    """The ctypes mirrors in julius_b200/desc.py must lay the descriptors out exactly as include/jb200_model.h does
+    (the product library, the plugin and the oracle all read them through that header)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from julius_b200 import desc
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    fields = {"jb200_tree_desc": (desc.TreeDesc, ["n_nodes", "lm_unk_num_log", "self_a", "bi_prob", "lm_type", "penalty1", "init_word", "cp_allowed"]),
+              "jb200_gmm_desc": (desc.GmmDesc, ["n_states", "state_off", "valid", "cd_states"]),
+              "jb200_dnn_desc": (desc.DnnDesc, ["n_layers", "layer_out", "w", "state_prior"])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "jb200_model.h"', 'int main(void) {']
+    for st, (_, names) in fields.items():
+        src.append(f'  printf("{st} %zu", sizeof({st}));')
+        for n in names:
+            src.append(f'  printf(" %zu", offsetof({st}, {n}));')
+        src.append('  printf("\\n");')
+    src.append('  return 0; }')
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(cfile)], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    for line in out:
+        if not line.strip():
+            continue
+        parts = line.split()
+        cls, names = fields[parts[0]]
+        want = [C.sizeof(cls)] + [getattr(cls, n).offset for n in names]
+        assert [int(x) for x in parts[1:]] == want, parts[0]

@@ -26,6 +26,27 @@ SWEEP = [
 ]
 
 
+GRAMMAR_SWEEP = [["-b", "100"], ["-b", "60", "-penalty1", "-2.5", "-iwcd1", "max"], ["-b", "150", "-multipath", "-penalty1", "1.5"]]
+
+
+@pytest.mark.skipif(not os.path.exists(JREF), reason="compiled reference (oracle/_ref/jref) not present")
+@pytest.mark.parametrize("extra", GRAMMAR_SWEEP, ids=[" ".join(e) for e in GRAMMAR_SWEEP])
+def test_grammar_mode_restatement_equals_compiled_reference(extra, tmp_path, oracle_lib):
+    """Grammar (DFA) recognition: category tree, category-pair constraint, insertion penalty, all sentence-initial
+    words alive at frame 0, best atom of the last frame as the pass-1 result (beam.c:1669-1760, :2404-2455, :435-458)."""
+    from oracle import fixtures
+    d = str(tmp_path)
+    m, files, dump, out = fixtures.make_fixture("small", d, n_utts=2, n_frames=180, extra_args=extra, noise_utts=1, grammar=True)
+    ds = desc.Descriptors(refdump.load_blob(os.path.join(d, "model.jb2m")))
+    assert ds.tree.lm_type == 1 and ds.tree.n_shared == 0 and ds.tree.n_init >= 1
+    for u in refdump.load_refdump(dump):
+        r = oracle_lib.beam_decode(ds, u.outprob)
+        ok, why = atoms_equal(r["atoms"], u.atoms)
+        assert ok, why
+        assert r["words"] == u.words and r["status"] == u.status
+        assert np.float32(r["score"]) == np.float32(u.score)
+
+
 @pytest.mark.skipif(not os.path.exists(JREF), reason="compiled reference (oracle/_ref/jref) not present")
 def test_tied_mixture_with_history_dependent_pruning_is_refused(tmp_path):
     """-gprune beam (the default) on a tied-mixture AM seeds each codebook's pruning with the previous frame's best

@@ -10,7 +10,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = ["tiny", "small_b100", "small_safe", "small_mp", "small_iwsp"]
 DNN_CASES = ["small_dnn", "small_dnn_iwsp"]
 # pinned on the CPU only so far (the GPU suite does not run them yet)
-ORACLE_ONLY_CASES = ["small_tr", "small_tm"]
+ORACLE_ONLY_CASES = ["small_tr", "small_tm", "small_dfa"]
 
 
 class Golden:
