@@ -3,8 +3,9 @@
 // Stands in for libjulius/src/beam.c get_back_trellis_init/_proceed/_end + finalize_1st_pass
 // (:1825, :2663, :3052, :3133), outprob_style (outprob_style.c:354-494), the factoring look-ups
 // (factoring_sub.c:942-1143, ngram_access.c:249-305) and the word-trellis store/sort
-// (backtrellis.c:190-267,438-478), for N-gram LMs, stock "fast" switches; normal trees (beam_kernel) and
-// multipath trees (beam_kernel_mp).
+// (backtrellis.c:190-267,438-478), stock "fast" switches: N-gram LMs on normal trees (beam_kernel, body in
+// beam_frames.inc) and multipath trees (beam_kernel_mp); DFA grammars on the category tree (beam_kernel_grammar = the
+// same body with the three grammar-mode differences compiled in; opt-in until it has run against the oracle on a device).
 //
 // Why this is not a transliteration.  The reference walks the survivors of frame t-1 one by one
 // and lets each arc "propagate" into a per-node slot; ties are won by whoever arrived first, new
@@ -106,6 +107,8 @@ struct BeamParams {
   unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine;
   unsigned long long *lmc; int lmc_bits;      // memo of max_successor_prob, 2^lmc_bits entries (0 = off)
   int maxt, maxc, maxw, maxbits;
+  // grammar (DFA) mode, appended so that the offsets of everything above stay what the N-gram kernels were built with
+  const uint8_t *cp_allowed; const int *init_node; const float *init_lscore; int n_init; float penalty1;
 };
 
 // ---- small device helpers ----------------------------------------------------------------------
@@ -532,502 +535,93 @@ __device__ __forceinline__ void finalize_utt(const BeamParams &p, const int u, c
   }
 }
 
+// The same for grammar (DFA) mode: the pass-1 result is the best atom of the last frame that holds any
+// (find_1pass_result, beam.c:435-458), whatever its word.
+__device__ __forceinline__ void finalize_utt_grammar(const BeamParams &p, const int u, const int tid, const int T, jb200_atom *araw, int *newidx,
+                                             const int *group0, jb200_utt_result *res, int *words,
+                                             int &s_natoms, int &s_overflow, int &s_found, long long &s_outbase,
+                                             long long *s_prof, long long &s_tprev) {
+  // ================= finalize_1st_pass: bt_relocate_rw + bt_sort_rw (backtrellis.c:218-267,438-478) ====
+  // group g = atoms with end frame g (raw atoms are grouped by creation frame already);
+  // inside a group order by word id (unique per group in this build: one token per node).
+  const int natoms = s_natoms;
+  for (int a = tid; a < natoms; a += BEAM_THREADS) {
+    const jb200_atom me = araw[a];
+    const int lo = group0[me.endtime], hi = group0[me.endtime + 1];
+    int rank = 0;
+    for (int b = lo; b < hi; b++) rank += (araw[b].wid < me.wid) ? 1 : 0;
+    newidx[a] = lo + rank;
+  }
+  if (tid == 0) {
+    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
+    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
+    else s_outbase = (long long)base;
+  }
+  __syncthreads();
+  const long long ob = s_outbase;
+  const bool can_write = (ob >= 0);
+  const int kept = can_write ? natoms : 0;
+  for (int a = tid; a < kept; a += BEAM_THREADS) {
+    jb200_atom me = araw[a];
+    me.last = (me.last < 0) ? -1 : newidx[me.last];
+    p.atoms_out[ob + newidx[a]] = me;
+    // find_1pass_result (beam.c:394-424): the latest end frame holding a </s> atom
+    if (me.backscore > JB200_LOG_ZERO) atomicMax(&s_found, me.endtime);
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  if (tid == 0) {
+    int status = 0, nw = 0; float score = 0.0f;
+    const int last_time = s_found;
+    if (kept == 0 || last_time < 0) status = -1;
+    else {
+      // the unique </s> atom of group last_time
+      const int lo = group0[last_time], hi = group0[last_time + 1];
+      int best = -1; float maxscore = JB200_LOG_ZERO;
+      for (int b = lo; b < hi; b++) {                      // rw[last_time][] order = word id order; strict '<' keeps the first maximum
+        const jb200_atom x = p.atoms_out[ob + b];
+        if (maxscore < x.backscore) { maxscore = x.backscore; best = b; }
+      }
+      if (best < 0) status = -1;
+      else {
+        // trace_backptr (beam.c:253-301)
+        int tmp[MAX_WORDS]; int n = 0; int a = best;
+        tmp[n++] = p.atoms_out[ob + a].wid;
+        while (p.atoms_out[ob + a].begintime > 0) {
+          a = p.atoms_out[ob + a].last;
+          if (a < 0 || n >= MAX_WORDS) break;
+          tmp[n++] = p.atoms_out[ob + a].wid;
+        }
+        for (int i = 0; i < n; i++) words[i] = tmp[n - i - 1];
+        nw = n; score = p.atoms_out[ob + best].backscore;
+      }
+    }
+    jb200_utt_result r;
+    r.status = status; r.n_frames = T; r.n_atoms = kept; r.n_words = nw; r.score = score;
+    r.atom_offset = ob; r.word_offset = u * MAX_WORDS; r.overflow = s_overflow;
+    *res = r;
+    PROF_MARK(7);
+    if (p.prof) for (int k = 0; k < 8; k++) p.prof[(size_t)u * 8 + k] = s_prof[k];
+  }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char beam_smem[];
 
 #ifndef JB200_BEAM_MINBLOCKS
 #define JB200_BEAM_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(BEAM_THREADS, JB200_BEAM_MINBLOCKS)
-beam_kernel(const BeamParams p) {
-  const int u = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
-  const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
-
-  unsigned long long *heap = reinterpret_cast<unsigned long long *>(beam_smem);   // [MAXT+4] heap entries, slot h = heap index h
-  int *offs = reinterpret_cast<int *>(heap + MAXT + 4);                           // [beam+2] candidate payload offsets per survivor
-  int *poff = offs + (p.beam + 2);                                                // [beam+2] arrival-order bit positions per survivor
-  __shared__ int s_warp[NWARP + 1];
-  __shared__ int s_ncre, s_E, s_natoms, s_ns, s_cur, s_overflow, s_found, s_flag;
-  __shared__ unsigned s_pmaxkey, s_losekey;
-  __shared__ unsigned long long s_webest;
-  __shared__ float s_thr;
-  __shared__ long long s_outbase;
-  __shared__ long long s_prof[8], s_tprev;
-
-  Tok *tok0 = p.tok + (size_t)u * 2 * MAXT;
-  int *ord0 = p.order + (size_t)u * 2 * MAXT;
-  const SlotView slots{p.slots + (size_t)u * p.n_nodes};
-  Cand *cand = p.cand + (size_t)u * MAXC;
-  CandB *candb = p.candb + (size_t)u * MAXC;
-  Tok *surv = p.surv + (size_t)u * (p.beam + 2);       // the survivors of the previous frame, in visiting order
-  IsoCand *iso = p.iso + (size_t)u * max(p.n_iso, 1);
-  WEnd *wend = p.wend + (size_t)u * MAXW;
-  unsigned *bits = p.bitmask + (size_t)u * (p.maxbits >> 5);
-  int *wpre = p.wordpre + (size_t)u * (p.maxbits >> 5);
-  unsigned long long *outv = p.outv + (size_t)u * (p.beam + 1);
-  const long long a0 = p.atom_off[u];
-  const int atom_cap = (int)(p.atom_off[u + 1] - a0);
-  jb200_atom *araw = p.atoms_raw + a0;
-  int *newidx = p.newidx + a0;
-  int *group0 = p.group0 + (size_t)f_begin + u;          // [T+1]: first raw atom of end-frame group g
-  int *counts = p.counts + (size_t)f_begin * 2;
-  jb200_utt_result *res = p.results + u;
-  int *words = p.words + (size_t)u * MAX_WORDS;
-
-  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1;
-                  for (int k = 0; k < 8; k++) s_prof[k] = 0; s_tprev = clock64(); }
-  __syncthreads();
-
-  // ================= frame 0: init_nodescore (beam.c:1631-1665) + first sort (:1883) =================
-  if (T > 0 && tid == 0) {
-    const int node = p.head_node;
-    const NodeRec nr = p.nodes[node];
-    Tok tk;
-    float ll = (nr.scid != 0) ? max_successor_prob(p, -1, nr.scid) : 0.0f;
-    ll = ll * p.lm_weight + p.lm_penalty;
-    tk.lscore = ll; tk.tre = -1; tk.cword = -1; tk.tre_wid = -1; tk.node = node;
-    tk.score = outprob_style(p, p.rows + (size_t)f_begin * p.row_stride, nr.out, -1) + ll;
-    tok0[0] = tk;
-    surv[0] = tk;
-    ord0[0] = 0;
-    s_ns = 1;
-    counts[0] = 1; counts[1] = 1;
-  }
-  __syncthreads();
-
-  int tnum_prev = (T > 0) ? 1 : 0;      // tokens created in the previous frame (clear phase)
-  int groups = T;                       // number of end-frame groups kept by finalize (framelen)
-  bool slots_clean = false;             // the previous frame's node slots were already reset under its beam cut
-
-  // ================= frames 1..T-1: get_back_trellis_proceed (beam.c:2663-3019) =================
-  for (int t = 1; t < T; t++) {
-    const int cur = s_cur, nxt = cur ^ 1;
-    Tok *tl = tok0 + (size_t)cur * MAXT, *tn = tok0 + (size_t)nxt * MAXT;
-    int *ordl = ord0 + (size_t)cur * MAXT, *ordn = ord0 + (size_t)nxt * MAXT;
-    const int ns = s_ns;
-    const float thr = s_thr;
-    const float *row = p.rows + (size_t)(f_begin + t) * p.row_stride;
-
-    // ---- P0: clear_tokens (beam.c:1122): reset the node slots used by frame t-1 (normally done already by
-    //          the idle warps while thread 0 replayed that frame's heap select, see P6)
-    if (!slots_clean) {
-      for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
-        const int node = tl[i].node;
-        slots.reset(node);
-      }
-    }
-    slots_clean = false;
-    if (tid == 0) { s_ncre = 0; s_webest = 0ull; s_pmaxkey = 0u; group0[t - 1] = s_natoms; }
-    __syncthreads();
-    PROF_MARK(0);
-
-    // ---- P1: per survivor: candidate counts, word ends, trellis atoms (save_trellis, beam.c:2209)
-    int cand_total, nbits;
-    {
-      int carry_c = 0, carry_a = s_natoms, carry_w = 0;
-      for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
-        const int j = j0 + tid;
-        int nin = 0, is_we = 0, is_tr = 0;
-        Tok tk; NodeRec nr;
-        if (j < ns) {
-          tk = surv[j];
-          nr = p.nodes[tk.node];
-          const bool valid = (tk.score > JB200_LOG_ZERO) && !(tk.score < thr);
-          if (valid) {
-            nin = (nr.self_a != JB200_LOG_ZERO) + (nr.next_a != JB200_LOG_ZERO) + nr.arc_n;
-            if (nr.stend >= 0) { is_we = 1; is_tr = (nr.stend != p.tail_silwid); }
-          }
-        }
-        int tot_c, tot_a, tot_w;
-        const int oc = block_excl_scan(nin, s_warp, &tot_c);
-        const int oa = block_excl_scan(is_we, s_warp, &tot_a);
-        const int ow = block_excl_scan(is_tr, s_warp, &tot_w);
-        if (j < ns) {
-          offs[j] = carry_c + oc;
-          // arrival-order position of this survivor's first candidate: its word-internal arcs,
-          // then (for a word end that may continue) one slot per isolated root
-          poff[j] = carry_c + oc + (carry_w + ow) * p.n_iso;
-          if (is_we) {
-            const int ai = carry_a + oa;
-            if (ai < atom_cap) {
-              jb200_atom a;
-              a.wid = nr.stend; a.backscore = tk.score;
-              a.begintime = (tk.tre < 0 ? -1 : araw[tk.tre].endtime) + 1;
-              a.endtime = t - 1; a.last = tk.tre; a.lscore = tk.lscore;
-              araw[ai] = a;
-            } else s_overflow = 1;
-            if (is_tr) {
-              const int wi = carry_w + ow;
-              if (wi < MAXW && ai < atom_cap) {
-                WEnd w;
-                const int sword = nr.stend;
-                const int transp = p.is_transp[sword];
-                w.j = j; w.atom = ai; w.last_word = transp ? tk.cword : sword;
-                w.base = tk.score + __ldg(p.wordend_a + sword);
-                w.transp2 = (transp && tk.cword >= 0 && p.is_transp[tk.cword]) ? 1 : 0;
-                w.nintra = nin;
-                wend[wi] = w;
-                if (w.base > JB200_LOG_ZERO)   // beam.c:2308 keeps the FIRST maximum
-                  atomicMax(&s_webest, ((unsigned long long)fkey(w.base) << 32) | (unsigned)(~(unsigned)wi));
-              } else s_overflow = 1;
-            }
-          }
-        }
-        carry_c += tot_c; carry_a += tot_a; carry_w += tot_w;
-      }
-      cand_total = carry_c;
-      nbits = carry_c + carry_w * p.n_iso + p.n_shared;
-      if (tid == 0) { offs[ns] = carry_c; poff[ns] = carry_c + carry_w * p.n_iso; s_natoms = min(carry_a, atom_cap); s_E = min(carry_w, MAXW); }
-      if (cand_total > MAXC || carry_w > MAXW || nbits > p.maxbits) { if (tid == 0) s_overflow = 1; cand_total = 0; nbits = 0; }
-    }
-    const int nwords = (nbits + 31) >> 5;
-    for (int w = tid; w < nwords; w += BEAM_THREADS) bits[w] = 0u;
-    __syncthreads();
-    PROF_MARK(1);
-    const int E = (nbits > 0) ? s_E : 0;
-
-    // ---- P2a: word-internal transitions (beam_intra_word(_core), beam.c:2004-2177), one thread per
-    //           candidate (survivors near the tree roots fan out 10-20 ways: per-survivor loops leave most
-    //           of the block idle); the owner of candidate c is found by bisection of the offsets
-    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
-      int lo = 0, hi = ns;
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= c) lo = mid; else hi = mid; }
-      const int j = lo;
-      int k = c - offs[j];
-      const Tok tk = surv[j];
-      const NodeRec nr = p.nodes[tk.node];
-      int next; float pa;
-      const int has_self = (nr.self_a != JB200_LOG_ZERO), has_next = (nr.next_a != JB200_LOG_ZERO);
-      if (has_self && k == 0) { next = tk.node; pa = nr.self_a; }
-      else if (has_next && k == has_self) { next = tk.node + 1; pa = nr.next_a; }
-      else { const int a = k - has_self - has_next; next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
-      float tmpsum = tk.score + pa;
-      float lsc = JB200_LOG_ZERO;
-      int out_next = nr.out;
-      if (next != tk.node) {
-        const int2 so = __ldg(reinterpret_cast<const int2 *>(&p.nodes[next].scid));
-        const int scid = so.x;
-        out_next = so.y;
-        if (scid != 0) {
-          lsc = max_successor_prob(p, tk.cword, scid) * p.lm_weight + p.lm_penalty;
-          tmpsum -= tk.lscore;
-          tmpsum += lsc;
-        }
-      }
-      if (lsc == JB200_LOG_ZERO) lsc = tk.lscore;
-      Cand cd; cd.score = tmpsum; cd.node = next; cd.lscore = lsc; cd.src = j;
-      cand[c] = cd;
-      CandB cb; cb.tre = tk.tre; cb.cword = tk.cword; cb.tre_wid = tk.tre_wid; cb.out = out_next;
-      candb[c] = cb;
-      if (tmpsum > JB200_LOG_ZERO) {
-        const unsigned seq = (unsigned)j * SEQ_LOCAL + (unsigned)k;
-        cand_atomics(slots, next, tmpsum, seq, seq);
-      }
-    }
-    if (p.prof_fine) { __syncthreads(); PROF_MARK(4); }
-    // ---- P2b: cross-word transitions into isolated roots (beam_inter_word, beam.c:2271-2517),
-    //           pre-reduced per root over this frame's word ends, visited in survivor order
-    for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
-      const int col = __ldg(p.iso_id + i);
-      float best = JB200_LOG_ZERO, bestl = 0.0f; int beste = -1, firste = -1;
-      for (int e = 0; e < E; e++) {
-        const WEnd w = wend[e];
-        const float tmpprob = __ldg(p.iw + (size_t)w.last_word * p.n_iso + col);
-        const float lsc = tmpprob * p.lm_weight + p.lm_penalty;
-        float tmpsum = w.base;
-        tmpsum += lsc;
-        if (w.transp2) tmpsum += p.lm_penalty_trans;
-        if (tmpsum > JB200_LOG_ZERO) {
-          if (firste < 0) firste = e;
-          if (beste < 0 || best < tmpsum) { best = tmpsum; beste = e; bestl = lsc; }
-        }
-      }
-      IsoCand ic; ic.score = best; ic.e = beste; ic.lscore = bestl; ic.first_e = firste;
-      iso[i] = ic;
-      if (firste >= 0) {
-        const WEnd wf = wend[firste], wb = wend[beste];
-        const unsigned sf = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
-        const unsigned sw = (unsigned)wb.j * SEQ_LOCAL + (unsigned)(wb.nintra + i);
-        cand_atomics(slots, __ldg(p.iso_node + i), best, sf, sw);
-      }
-    }
-    // ---- P2c: best word end -> shared (1-gram factored) roots (beam_inter_word_factoring, :2549-2616)
-    const unsigned long long webest = s_webest;
-    const bool have_we = (webest != 0ull) && (nbits > 0);
-    WEnd wbest; wbest.base = 0.0f; wbest.atom = -1; wbest.last_word = -1; wbest.transp2 = 0; wbest.j = 0; wbest.nintra = 0;
-    if (have_we) {
-      wbest = wend[(unsigned)(~(unsigned)(webest & 0xffffffffu))];
-      for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
-        const float lsc = __ldg(p.shared_f + i) * p.lm_weight + p.lm_penalty;
-        float tmpsum = wbest.base;
-        tmpsum += lsc;
-        if (wbest.transp2) tmpsum += p.lm_penalty_trans;
-        if (tmpsum < thr) continue;
-        if (tmpsum > JB200_LOG_ZERO) {
-          const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
-          cand_atomics(slots, __ldg(p.shared_node + i), tmpsum, seq, seq);
-        }
-      }
-    }
-    __syncthreads();
-    PROF_MARK(2);
-
-    // ---- P3: creators = candidates that were the first to reach their node; one bit each at the
-    //          candidate's position in sequential arrival order
-    for (int c = tid; c < cand_total; c += BEAM_THREADS) {
-      const Cand cd = cand[c];
-      if (!(cd.score > JB200_LOG_ZERO)) continue;
-      const int k = c - offs[cd.src];
-      const unsigned seq = (unsigned)cd.src * SEQ_LOCAL + (unsigned)k;
-      if ((unsigned)__ldcg(slots.fs(cd.node)) == seq) {
-        const int pos = poff[cd.src] + k;
-        atomicOr(bits + (pos >> 5), 1u << (pos & 31));
-      }
-    }
-    for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
-      const IsoCand ic = iso[i];
-      if (ic.first_e < 0) continue;
-      const WEnd wf = wend[ic.first_e];
-      const unsigned seq = (unsigned)wf.j * SEQ_LOCAL + (unsigned)(wf.nintra + i);
-      if ((unsigned)__ldcg(slots.fs(__ldg(p.iso_node + i))) == seq) {
-        const int pos = poff[wf.j] + wf.nintra + i;
-        atomicOr(bits + (pos >> 5), 1u << (pos & 31));
-      }
-    }
-    if (have_we) {
-      for (int i = tid; i < p.n_shared; i += BEAM_THREADS) {
-        const unsigned seq = (unsigned)ns * SEQ_LOCAL + (unsigned)i;
-        if ((unsigned)__ldcg(slots.fs(__ldg(p.shared_node + i))) == seq) {
-          const int pos = poff[ns] + i;
-          atomicOr(bits + (pos >> 5), 1u << (pos & 31));
-        }
-      }
-    }
-    __syncthreads();
-    PROF_MARK(3);
-
-    // ---- P4: creation order (create_token numbering, beam.c:1147-1162) = rank of the set bits
-    int ncre;
-    {
-      int carry = 0;
-      for (int w0 = 0; w0 < nwords; w0 += BEAM_THREADS) {
-        const int w = w0 + tid;
-        const int cnt = (w < nwords) ? __popc(__ldcg(bits + w)) : 0;
-        int tot;
-        const int ex = block_excl_scan(cnt, s_warp, &tot);
-        if (w < nwords) wpre[w] = carry + ex;
-        carry += tot;
-      }
-      ncre = carry;
-    }
-    if (ncre > MAXT) { if (tid == 0) s_overflow = 1; ncre = 0; }
-    __syncthreads();
-    PROF_MARK(4);
-
-    // ---- P5: materialise tokens with the winner's content, add the output probability (beam.c:2944)
-    auto materialise = [&](int pos, int node) {
-      const unsigned wbits = __ldcg(bits + (pos >> 5));
-      if (!((wbits >> (pos & 31)) & 1u)) return;
-      const int r = wpre[pos >> 5] + __popc(wbits & ((1u << (pos & 31)) - 1u));
-      const unsigned long long bk = __ldcg(slots.bk(node));
-      const unsigned seqw = ~(unsigned)(bk & 0xffffffffu);
-      const int j = (int)(seqw >> SEQ_LOCAL_BITS), local = (int)(seqw & (SEQ_LOCAL - 1));
-      Tok nt; nt.node = node;
-      int out;
-      if (j == ns) {                                    // factoring pass
-        const float lsc = __ldg(p.shared_f + local) * p.lm_weight + p.lm_penalty;
-        float tmpsum = wbest.base; tmpsum += lsc;
-        if (wbest.transp2) tmpsum += p.lm_penalty_trans;
-        nt.score = tmpsum; nt.lscore = lsc; nt.tre = wbest.atom; nt.cword = wbest.last_word;
-        nt.tre_wid = araw[wbest.atom].wid;
-        out = p.nodes[node].out;
-      } else {
-        const int c0 = offs[j], nin = offs[j + 1] - c0;
-        if (local < nin) {                              // word-internal candidate: everything travels with it
-          const Cand cd = cand[c0 + local];
-          const CandB cb = candb[c0 + local];
-          nt.score = cd.score; nt.lscore = cd.lscore; nt.tre = cb.tre; nt.cword = cb.cword; nt.tre_wid = cb.tre_wid;
-          out = cb.out;
-        } else {                                        // isolated-root candidate
-          const IsoCand ic = iso[local - nin];
-          const WEnd w = wend[ic.e];
-          nt.score = ic.score; nt.lscore = ic.lscore; nt.tre = w.atom; nt.cword = w.last_word;
-          nt.tre_wid = araw[w.atom].wid;
-          out = p.nodes[node].out;
-        }
-      }
-      nt.score += outprob_style(p, row, out, nt.tre_wid);
-      tn[r] = nt;
-      heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(nt.score);
-      atomicMax(&s_pmaxkey, fkey(nt.score));
-    };
-    if (ncre > 0) {
-      for (int c = tid; c < cand_total; c += BEAM_THREADS) {
-        const Cand cd = cand[c];
-        if (!(cd.score > JB200_LOG_ZERO)) continue;
-        materialise(poff[cd.src] + (c - offs[cd.src]), cd.node);
-      }
-      for (int i = tid; i < p.n_iso; i += BEAM_THREADS) {
-        const IsoCand ic = iso[i];
-        if (ic.first_e < 0) continue;
-        const WEnd wf = wend[ic.first_e];
-        materialise(poff[wf.j] + wf.nintra + i, __ldg(p.iso_node + i));
-      }
-      if (have_we)
-        for (int i = tid; i < p.n_shared; i += BEAM_THREADS) materialise(poff[ns] + i, __ldg(p.shared_node + i));
-    }
-    __syncthreads();
-    PROF_MARK(5);
-
-    // ---- P6: beam cut = the reference's heap select (sort_token_no_order, beam.c:1492-1520)
-    int ns_new;
-    {
-      const int need = p.beam, rest = ncre - need;
-      if (need >= ncre) {
-        ns_new = ncre;
-        for (int k = tid; k < ns_new; k += BEAM_THREADS) ordn[k] = k;
-      } else {
-        const bool upward = (need < rest);
-        const int extract = upward ? need : rest;
-        ns_new = need;
-        bool ok = false;
-        // the node slots of this frame are dead from here on: warps 1.. reset them for the next frame while
-        // thread 0 is busy with the extraction replay (SlotClear, run inside heap_extract_fast*)
-        const SlotClear sc{tn, ncre, slots};
-        if (p.force_seq_heap) sc.run((int)threadIdx.x, BEAM_THREADS);
-        slots_clean = true;
-        if (!p.force_seq_heap) {
-          if (upward) {
-            // lower bound of the need-th largest score from a 1024-bin histogram of the order-preserving
-            // keys (bin width ~0.5 in score units, adapted to the magnitude of the best score)
-            constexpr int NB = 1024;
-            int *hist = offs;                          // offs/poff are dead after P5
-            const int nb = min(NB, 2 * (p.beam + 2));
-            for (int i = tid; i < nb; i += BEAM_THREADS) hist[i] = 0;
-            __syncthreads();
-            const unsigned maxkey = s_pmaxkey;
-            const int e = (int)((((maxkey & 0x80000000u) ? (maxkey & 0x7fffffffu) : ~maxkey) >> 23) & 0xffu) - 127;
-            const int sh = max(0, min(24, 22 - e));
-            for (int r = tid; r < ncre; r += BEAM_THREADS) {
-              const unsigned key = fkey(hval(heap[r + 1]));
-              const unsigned bin = min((unsigned)(nb - 1), (maxkey - key) >> sh);
-              atomicAdd(&hist[bin], 1);
-            }
-            __syncthreads();
-            if (tid < 32) {
-              int cum = 0, found = -1;
-              for (int b0 = 0; b0 < nb && found < 0; b0 += 32) {
-                const int v = (b0 + tid < nb) ? hist[b0 + tid] : 0;
-                int x = v;
-                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
-                const unsigned hit = __ballot_sync(0xffffffffu, cum + x >= need);
-                if (hit) found = b0 + __ffs(hit) - 1;
-                cum += __shfl_sync(0xffffffffu, x, 31);
-              }
-              if (tid == 0) {
-                unsigned lk = 0u;
-                if (found >= 0 && found < nb - 1) {
-                  const unsigned long long drop = (unsigned long long)(found + 1) << sh;
-                  lk = (drop < maxkey) ? maxkey - (unsigned)drop : 0u;
-                }
-                s_losekey = lk;
-              }
-            }
-            __syncthreads();
-            const unsigned lk = s_losekey;
-            const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
-            heap_pad_sentinels<true>(heap, ncre, MAXT);
-            heap_build<true>(heap, ncre); PROF_MARK(7);
-            heap_extract_fast<true>(heap, ncre, extract, lose_below, outv, MAXT, p.misspec_counter, &sc);
-          } else {
-            heap_pad_sentinels<false>(heap, ncre, MAXT);
-            heap_build<false>(heap, ncre); PROF_MARK(7);
-            heap_extract_fast<false>(heap, ncre, extract, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
-          }
-          ok = true;
-          if (ok) {
-            // survivors: upward = the extracted maxima, last extracted first (slots n-need+1..n);
-            //            downward = what is left of the heap (slots 1..need)
-            if (upward) for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
-            else for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
-          }
-        }
-        if (!ok || p.check_heap) {
-          // sequential replay from the token scores (JB200_FORCE_SEQ_HEAP, or self-check JB200_CHECK_HEAP)
-          __syncthreads();
-          for (int r = tid; r < ncre; r += BEAM_THREADS) heap[r + 1] = ((unsigned long long)(unsigned)r << 32) | __float_as_uint(tn[r].score);
-          __syncthreads();
-          if (upward) { heap_build<true>(heap, ncre); heap_extract_seq<true>(heap, ncre, extract); }
-          else { heap_build<false>(heap, ncre); heap_extract_seq<false>(heap, ncre, extract); }
-          const int start = upward ? ncre - need : 0;
-          for (int k = tid; k < need; k += BEAM_THREADS) {
-            const int id = (int)(heap[start + k + 1] >> 32);
-            if (ok && ordn[k] != id) s_overflow = 4;      // self-check: pipelined replay disagrees
-            ordn[k] = id;
-          }
-          if (!ok && tid == 0) atomicAdd(p.misspec_counter, 1ull);
-        }
-      }
-    }
-    // the survivors in visiting order, compact (every thread re-reads the order entries it wrote itself)
-    for (int k = tid; k < ns_new; k += BEAM_THREADS) surv[k] = tn[ordn[k]];
-    PROF_MARK(6);
-    if (tid == 0) {
-      counts[2 * t] = ncre; counts[2 * t + 1] = ns_new;
-      s_ns = ns_new; s_cur = nxt;
-      if (p.prune_width >= 0.0f && s_pmaxkey != 0u) {
-        const unsigned k = s_pmaxkey;
-        const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-        s_thr = __uint_as_float(b) - p.prune_width;
-      } else s_thr = JB200_LOG_ZERO;
-    }
-    tnum_prev = ncre;
-    __syncthreads();
-    if (ncre == 0) { groups = t; break; }      // beam.c:3012-3015: no nodes left, search terminated
-  }
-
-  // ================= get_back_trellis_end (normal version, beam.c:3076-3086) =================
-  {
-    const int cur = s_cur;
-    Tok *tl = tok0 + (size_t)cur * MAXT;
-    int *ordl = ord0 + (size_t)cur * MAXT;
-    const int ns = (T > 0) ? s_ns : 0;
-    if (tid == 0 && T > 0 && groups == T) group0[T - 1] = s_natoms;
-    __syncthreads();
-    int carry_a = s_natoms;
-    for (int j0 = 0; j0 < ns; j0 += BEAM_THREADS) {
-      const int j = j0 + tid;
-      int is_we = 0; Tok tk; int stend = -1;
-      if (j < ns) { tk = surv[j]; stend = p.nodes[tk.node].stend; is_we = (stend >= 0); }
-      int tot;
-      const int oa = block_excl_scan(is_we, s_warp, &tot);
-      if (is_we) {
-        const int ai = carry_a + oa;
-        if (ai < atom_cap) {
-          jb200_atom a;
-          a.wid = stend; a.backscore = tk.score;
-          a.begintime = (tk.tre < 0 ? -1 : araw[tk.tre].endtime) + 1;
-          a.endtime = T - 1; a.last = tk.tre; a.lscore = tk.lscore;     // save_trellis(t = samplenum)
-          araw[ai] = a;
-        } else s_overflow = 1;
-      }
-      carry_a += tot;
-    }
-    if (tid == 0) { s_natoms = min(carry_a, atom_cap); group0[groups] = s_natoms; }
-    // leave the node slots clean for the next utterance that uses this work area
-    if (!slots_clean) {
-      for (int i = tid; i < tnum_prev; i += BEAM_THREADS) {
-        const int node = tl[i].node;
-        slots.reset(node);
-      }
-    }
-    __syncthreads();
-  }
-
-  finalize_utt(p, u, tid, T, araw, newidx, group0, res, words, s_natoms, s_overflow, s_found, s_outbase, s_prof, s_tprev);
-}
+#define BEAM_KERNEL_NAME beam_kernel
+#define BEAM_GRAMMAR 0
+#include "beam_frames.inc"
+#undef BEAM_KERNEL_NAME
+#undef BEAM_GRAMMAR
+#define BEAM_KERNEL_NAME beam_kernel_grammar
+#define BEAM_GRAMMAR 1
+#include "beam_frames.inc"
+#undef BEAM_KERNEL_NAME
+#undef BEAM_GRAMMAR
 
 // ---- the multipath kernel ----------------------------------------------------------------------------
 // get_back_trellis_proceed, MULTIPATH branch (beam.c:2752-2828, :2930-2941).  Trees of multipath models
@@ -1616,6 +1210,7 @@ struct jb200_decoder {
   bool fetched = false;
   long long last_d2h = 0;
   int resident = 0;
+  bool grammar = false;
 };
 
 template <typename Tp>
@@ -1651,7 +1246,22 @@ extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
 
 extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int max_utts, int max_frames, jb200_decoder **out) {
   if (!t || !am || !out || max_utts < 1 || max_frames < 1) { set_error("jb200_decoder_create: bad argument"); return JB200_ERR_ARG; }
-  if (t->lm_type != JB200_LM_NGRAM) { set_error("grammar (DFA) lexicon trees are not supported by the GPU beam yet (lm_type %d)", t->lm_type); return JB200_ERR_UNSUPPORTED; }
+  const bool grammar = (t->lm_type == JB200_LM_DFA);
+  if (t->lm_type != JB200_LM_NGRAM && !grammar) { set_error("unknown language-model type %d", t->lm_type); return JB200_ERR_UNSUPPORTED; }
+  if (grammar) {
+    // beam_kernel_grammar is written against the pinned oracle but has not run on a device yet: opt-in only
+    if (!getenv("JB200_ENABLE_GRAMMAR") || atoi(getenv("JB200_ENABLE_GRAMMAR")) == 0) {
+      set_error("grammar (DFA) lexicon trees: the GPU kernel is not validated yet (set JB200_ENABLE_GRAMMAR=1 to try it)");
+      return JB200_ERR_UNSUPPORTED;
+    }
+    if (t->multipath) { set_error("grammar mode on a multipath tree is not supported by the GPU beam"); return JB200_ERR_UNSUPPORTED; }
+    if (t->n_shared != 0 || t->n_init < 1 || t->n_init > t->beam_width || !t->cp_allowed || !t->init_node || !t->init_lscore) {
+      set_error("grammar mode: inconsistent descriptor (n_shared %d, n_init %d, beam %d)", t->n_shared, t->n_init, t->beam_width);
+      return JB200_ERR_ARG;
+    }
+    for (int i = 0; i < t->n_words; i++)
+      if (t->is_transparent[i]) { set_error("grammar mode: transparent words are not supported"); return JB200_ERR_UNSUPPORTED; }
+  }
   if (t->n_nodes >= (1 << 28)) { set_error("lexicon tree too large"); return JB200_ERR_UNSUPPORTED; }
   if (t->beam_width < 1 || t->beam_width > 8000) { set_error("beam width %d outside 1..8000", t->beam_width); return JB200_ERR_UNSUPPORTED; }
   jb200_decoder *d = new jb200_decoder();
@@ -1702,6 +1312,13 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   }
   P.n_shared = t->n_shared;
   P.multipath = t->multipath ? 1 : 0;
+  P.cp_allowed = nullptr; P.init_node = nullptr; P.init_lscore = nullptr; P.n_init = 0; P.penalty1 = 0.0f;
+  if (grammar) {
+    TRY(dev_upload(d, t->cp_allowed, (size_t)t->n_words * t->n_iso, &P.cp_allowed));
+    TRY(dev_upload(d, t->init_node, (size_t)t->n_init, &P.init_node));
+    TRY(dev_upload(d, t->init_lscore, (size_t)t->n_init, &P.init_lscore));
+    P.n_init = t->n_init; P.penalty1 = t->penalty1;
+  }
   {
     // multipath: expand the roots into their successors (self, next, arcs: the order propagation visits them,
     // beam.c:2467-2500); the word-begin node of the head silence is never entered (beam.c:2336-2342)
@@ -1743,7 +1360,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.lm_mode = t->lm_mode; P.lm_unk_id = t->lm_unk_id; P.lm_unk_num_log = t->lm_unk_num_log;
   P.lm_weight = t->lm_weight; P.lm_penalty = t->lm_penalty; P.lm_penalty_trans = t->lm_penalty_trans;
   P.prune_width = t->score_pruning_width;
-  P.head_node = t->wordbegin[t->head_silwid]; P.tail_silwid = t->tail_silwid; P.beam = t->beam_width; P.n_nodes = n;
+  P.head_node = grammar ? 0 : t->wordbegin[t->head_silwid]; P.tail_silwid = t->tail_silwid; P.beam = t->beam_width; P.n_nodes = n;
   // cd sets come from the AM handle's descriptor: re-upload from the gmm handle is not exposed, so the
   // decoder asks the scorer for its device copies
   {
@@ -1758,7 +1375,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     float *iw = nullptr;
     TRY(dev_alloc(d, (size_t)t->n_words * std::max(t->n_iso, 1), &iw));
     P.iw = iw;
-    const long long tot = (long long)t->n_words * t->n_iso;
+    const long long tot = grammar ? 0 : (long long)t->n_words * t->n_iso;     // grammar mode reads cp_allowed instead
     if (tot > 0) {
       iw_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P, d_iso_word, iw, t->n_words);
       g_launches.fetch_add(1);
@@ -1827,7 +1444,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
   d->smem_bytes = (size_t)(maxt + 4) * 8 + (size_t)(t->beam_width + 2) * 4 * 2;
-  const void *kern = P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
+  d->grammar = grammar;
+  const void *kern = grammar ? (const void *)beam_kernel_grammar : P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
   TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
   {
     int per_sm = 0, sms = 0;
@@ -1870,7 +1488,8 @@ static int launch_beam(jb200_decoder *d, int n_utts) {
   P.rows = d->d_rows; P.row_stride = d->row_stride; P.frame_off = d->d_frame_off;
   P.atom_off = d->d_atom_off; P.atoms_out = d->d_atoms_out; P.atom_counter = d->d_atom_counter;
   P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words; P.prof = d->d_prof;
-  if (P.multipath) beam_kernel_mp<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
+  if (d->grammar) beam_kernel_grammar<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
+  else if (P.multipath) beam_kernel_mp<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   else beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   JB_LAUNCH_CHECK();
   return JB200_OK;

@@ -122,3 +122,25 @@ def test_forced_sequential_heap_gives_same_trellis(monkeypatch):
     dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
     for r, u in zip(dec.decode(g.feats), g.utts):
         _check(r, u)
+
+
+def test_grammar_mode_is_refused_without_opt_in(monkeypatch):
+    """tests/golden/small_dfa is a DFA-grammar model (category tree).  Its kernel (beam_kernel_grammar) is written
+    against the CPU-pinned oracle but has not been run on a device yet, so creation must fail loudly by default."""
+    monkeypatch.delenv("JB200_ENABLE_GRAMMAR", raising=False)
+    g = Golden("small_dfa")
+    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    with pytest.raises(capi.Jb200Error):
+        capi.Decoder(g.ds, am, max_utts=2, max_frames=512)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("JB200_ENABLE_GRAMMAR") != "1",
+                    reason="grammar-mode kernel is opt-in (JB200_ENABLE_GRAMMAR=1) until it has been validated on a device")
+def test_grammar_mode_trellis_matches_reference():
+    g = Golden("small_dfa")
+    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
+    for r, u in zip(dec.decode_scores([u.outprob for u in g.utts]), g.utts):
+        _check(r, u)
+    for r, u in zip(dec.decode(g.feats), g.utts):
+        _check(r, u)
