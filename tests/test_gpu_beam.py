@@ -144,3 +144,18 @@ def test_grammar_mode_trellis_matches_reference():
         _check(r, u)
     for r, u in zip(dec.decode(g.feats), g.utts):
         _check(r, u)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("JB200_GPU_EXTRA_CASES") != "1",
+                    reason="cases pinned on the CPU only so far; JB200_GPU_EXTRA_CASES=1 runs them on the device")
+@pytest.mark.parametrize("case", ["small_tr", "small_tm"])
+def test_cpu_pinned_cases_end_to_end_on_the_device(case):
+    """transparent (filler) words and the flattened tied-mixture model: host features -> GPU scores -> GPU beam."""
+    g = Golden(case)
+    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    for u, x in zip(g.utts, g.feats):
+        sc = am.score(x)
+        assert np.array_equal(sc.view(np.uint32), u.outprob.view(np.uint32))
+    dec = capi.Decoder(g.ds, am, max_utts=8, max_frames=4096)
+    for r, u in zip(dec.decode(g.feats), g.utts):
+        _check(r, u)
