@@ -420,6 +420,13 @@ dnn_softmax_kernel(const float *__restrict__ logits, int ld_logits, int N, const
 
 }  // namespace jb200
 
+namespace jb200 {
+// dnn_cluster.cu (experimental, JB200_DNN_KERNEL=2)
+int dnn_launch_cluster2(const CUtensorMap &ma_hi, const CUtensorMap &ma_lo, const CUtensorMap &mw_hi, const CUtensorMap &mw_lo,
+                        int M, int N, int K, const float *bias, const float *logistic, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo,
+                        int ld_out, float *logits, int ld_logits, int last, int n_sm, cudaStream_t st);
+}
+
 // =============================================================================================
 using namespace jb200;
 
@@ -524,7 +531,7 @@ extern "C" int jb200_dnn_create(const jb200_dnn_desc *d, int device, jb200_dnn *
   JB_CUDA(cudaFuncSetAttribute(dnn_gemm_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistentCfg<128>::SMEM));
   JB_CUDA(cudaFuncSetAttribute(dnn_gemm_persistent<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistentCfg<256>::SMEM));
   h->n_sm = prop.multiProcessorCount;
-  h->variant = getenv("JB200_DNN_KERNEL") ? atoi(getenv("JB200_DNN_KERNEL")) : 256;   // 0 one tile per CTA, 128 / 256 persistent
+  h->variant = getenv("JB200_DNN_KERNEL") ? atoi(getenv("JB200_DNN_KERNEL")) : 256;   // 0 one tile per CTA, 128 / 256 persistent, 2 = experimental 2-CTA cluster (dnn_cluster.cu)
   *out = h;
   return JB200_OK;
 }
@@ -578,6 +585,12 @@ int dnn_forward_device(jb200_dnn *h, const float *d_in, int T, float *d_rows, in
     } else if (h->variant == 128) {
       const int tiles = ((L.out + 127) / 128) * ((T + BM - 1) / BM);
       dnn_gemm_persistent<128><<<std::min(tiles, h->n_sm), GEMM_THREADS, PersistentCfg<128>::SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
+    } else if (h->variant == 2) {
+      rc = dnn_launch_cluster2(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g.M, g.N, g.K, g.bias, g.logistic, g.out_hi, g.out_lo,
+                               g.ld_out, g.logits, g.ld_logits, g.last, h->n_sm, st);
+      if (rc) return rc;
+      cur ^= 1;
+      continue;
     } else {
       const int tiles = ((L.out + 255) / 256) * ((T + BM - 1) / BM);
       dnn_gemm_persistent<256><<<std::min(tiles, h->n_sm), GEMM_THREADS, PersistentCfg<256>::SMEM, st>>>(ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, g);
