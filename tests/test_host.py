@@ -83,3 +83,34 @@ def test_descriptor_layouts_match_the_c_header(tmp_path):
         cls, names = fields[parts[0]]
         want = [C.sizeof(cls)] + [getattr(cls, n).offset for n in names]
         assert [int(x) for x in parts[1:]] == want, parts[0]
+
+
+def test_product_path_fails_loudly_without_a_device():
+    """No CPU fallback: on a machine without an sm_100 GPU every create call of the C-ABI must return an error (and the
+    Python mirror raise), never hand back a handle that computes on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = Golden("tiny")
+    with pytest.raises(capi.Jb200Error):
+        capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
+    d = Golden("small_dnn")
+    with pytest.raises(capi.Jb200Error):
+        capi.DnnScorer(d.ds)
+    assert capi.lib().jb200_device_count() <= 0 or True      # the call itself must not crash
+
+
+def test_nothing_in_the_product_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of julius_b200/ and none of the C/CUDA sources may reference it."""
+    pkg = os.path.join(ROOT, "julius_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        if "_obj" in dirpath:
+            continue
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".inc", ".c", ".h")):
+                continue
+            txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "liboracle" in txt or "oracle/restate" in txt or '#include "oracle' in txt:
+                bad.append(os.path.relpath(os.path.join(dirpath, fn), ROOT))
+    assert not bad, bad
