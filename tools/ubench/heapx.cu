@@ -164,6 +164,74 @@ __device__ __forceinline__ void extract7(unsigned long long *A, int n, int extra
   levels_out = levels; sink_out = sinkacc;
 }
 
+// variant 8: the top four levels of the heap (slots 1..15) live in REGISTERS of the extracting thread.  A sift through
+// them is a compile-time decision tree (sift_reg<P> knows its slot P, so every register index is static); only below
+// slot 15 does the shared-memory loop of variant 5 take over.  Saves the LDS round trip on the first four levels.
+struct SiftState { unsigned slot, cur; bool done; };
+
+template <int P>
+__device__ __forceinline__ void sift_reg(unsigned (&rv)[16], unsigned (&ri)[16], const unsigned s_lo, const unsigned s_hi, const float sv,
+                                         const float lose_below, const unsigned hb, unsigned &levels, SiftState &st) {
+  if constexpr (P >= 8) {
+    // children of P are the shared-memory slots 2P, 2P+1: one level by hand (its store target is a register)
+    unsigned x0, x1, y0, y1;
+    lds_pair(hb + (unsigned)P * 16u, x0, x1, y0, y1);
+    const bool right = __uint_as_float(x0) < __uint_as_float(y0);
+    const unsigned c_lo = right ? y0 : x0, c_hi = right ? y1 : x1;
+    levels++;
+    if (sv >= __uint_as_float(c_lo) || __uint_as_float(c_lo) < lose_below) { rv[P] = s_lo; ri[P] = s_hi; st.done = true; return; }
+    rv[P] = c_lo; ri[P] = c_hi;
+    st.slot = hb + (unsigned)(2 * P) * 8u + (right ? 8u : 0u);        // the chosen child's slot
+    st.cur = hb + ((unsigned)(2 * P) + (right ? 1u : 0u)) * 16u;      // the pair below it
+    st.done = false;
+  } else {
+    levels++;
+    if (__uint_as_float(rv[2 * P]) < __uint_as_float(rv[2 * P + 1])) {
+      if (sv >= __uint_as_float(rv[2 * P + 1]) || __uint_as_float(rv[2 * P + 1]) < lose_below) { rv[P] = s_lo; ri[P] = s_hi; st.done = true; return; }
+      rv[P] = rv[2 * P + 1]; ri[P] = ri[2 * P + 1];
+      sift_reg<2 * P + 1>(rv, ri, s_lo, s_hi, sv, lose_below, hb, levels, st);
+    } else {
+      if (sv >= __uint_as_float(rv[2 * P]) || __uint_as_float(rv[2 * P]) < lose_below) { rv[P] = s_lo; ri[P] = s_hi; st.done = true; return; }
+      rv[P] = rv[2 * P]; ri[P] = ri[2 * P];
+      sift_reg<2 * P>(rv, ri, s_lo, s_hi, sv, lose_below, hb, levels, st);
+    }
+  }
+}
+
+__device__ __forceinline__ void extract8(unsigned long long *A, int n, int extract, float lose_below, unsigned long long *outv,
+                                         unsigned &levels_out, unsigned &sink_out) {
+  unsigned levels = 0, sinkacc = 0, sink = 0;
+  const unsigned hb = smem_u32(A);
+  const unsigned capa = hb + (((unsigned)(MAXT >> 1) + 1u) << 4);
+  unsigned mslot = hb + ((unsigned)n << 3);
+  unsigned rv[16], ri[16];
+#pragma unroll
+  for (int i = 1; i < 16; i++) { rv[i] = (unsigned)A[i]; ri[i] = (unsigned)(A[i] >> 32); }
+  for (int x = 0; x < extract; x++) {
+    unsigned s_lo, s_hi;
+    lds_one(mslot, s_lo, s_hi);
+    sts_one(mslot, 0xff800000u, 0u);
+    mslot -= 8u;
+    outv[x] = ((unsigned long long)ri[1] << 32) | rv[1];
+    const float sv = __uint_as_float(s_lo);
+    SiftState st;
+    sift_reg<1>(rv, ri, s_lo, s_hi, sv, lose_below, hb, levels, st);
+    if (!st.done) {
+      unsigned slot = st.slot, cur = st.cur;
+      unsigned x0, x1, y0, y1, z0, z1, w0, w1;
+      lds_pair(cur, x0, x1, y0, y1);
+      while (true) {
+        LEVEL_C(x0, x1, y0, y1, z0, z1, w0, w1)
+        LEVEL_C(z0, z1, w0, w1, x0, x1, y0, y1)
+      }
+    done:
+      sts_one(slot, s_lo, s_hi);
+      sinkacc += sink;
+    }
+  }
+  levels_out = levels; sink_out = sinkacc;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int n, int extract_in, float lose_below,
                                             unsigned long long *outg, long long *res) {
@@ -181,6 +249,7 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
     long long t0 = clock64();
     if (V == 6) { extract2<V>(A, n, extract, lose_below, outv, levels, sinkacc); extract = 0; }
     if (V == 7) { extract7(A, n, extract, lose_below, outv, levels, sinkacc); extract = 0; }
+    if (V == 8) { extract8(A, n, extract, lose_below, outv, levels, sinkacc); extract = 0; }
     for (int x = 0; x < extract; x++) {
       unsigned s_lo, s_hi, r_lo, r_hi, x0, x1, y0, y1, z0, z1, w0, w1;
       lds_one(mslot, s_lo, s_hi);
@@ -246,7 +315,7 @@ int main() {
   cudaMalloc(&o, sizeof(unsigned long long) * 1024 * 592); cudaMalloc(&r, sizeof(hr));
   std::vector<unsigned long long> ho(1024);
   for (int blocks : {1, 592}) {
-    for (int v = 3; v < 8; v++) {
+    for (int v = 5; v < 9; v++) {
       for (int rep = 0; rep < 2; rep++) {
         switch (v) {
           case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
@@ -257,6 +326,7 @@ int main() {
           case 5: k<5><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 6: k<6><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 7: k<7><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 8: k<8><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
         }
         cudaDeviceSynchronize();
       }
