@@ -102,6 +102,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_source_sha() -> str:
+    """identity of the CUDA sources a committed ncu capture belongs to"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "julius_b200", "csrc")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith((".cu", ".cuh", ".inc")):
+            h.update(open(os.path.join(d, fn), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -111,10 +122,56 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------- reference arm
-def run_reference_sample(workload_name: str, n_procs: int, utts_per_proc: int, n_frames: int, seed: int):
-    """Decode utts_per_proc utterances in each of n_procs independent reference processes.
-    Returns (frames, seconds): seconds = the slowest process' time between PASS1_BEGIN and PASS1_END."""
-    from julius_b200 import synth, workload
+def host_cpus() -> dict:
+    """What this process may actually use: affinity mask and cgroup CPU quota, not os.cpu_count()."""
+    info = {"cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["cpu_count"]
+    quota = None
+    try:                                                  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:                                              # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    info["cgroup_quota"] = quota
+    tpc = 1
+    try:
+        sib = open("/sys/devices/system/cpu/cpu0/topology/thread_siblings_list").read().strip()
+        tpc = max(1, len([x for part in sib.split(",") for x in ([part] if "-" not in part else
+                                                                 range(int(part.split("-")[0]), int(part.split("-")[1]) + 1))]))
+    except Exception:
+        pass
+    info["threads_per_core"] = tpc
+    usable = info["affinity"] if quota is None else max(1, min(info["affinity"], int(quota)))
+    info["usable_threads"] = usable
+    return info
+
+
+def ref_procs(info: dict | None = None) -> int:
+    """One reference process per physical core this process may use: the decoder is single-threaded and
+    memory-bound, one per hardware thread is slower in aggregate (measured on a B200 box: 64 processes
+    6.2k frames/s, 128 processes 3.5k frames/s).  JB200_REF_PROCS overrides."""
+    if os.environ.get("JB200_REF_PROCS"):
+        return max(1, int(os.environ["JB200_REF_PROCS"]))
+    info = info or host_cpus()
+    u = info["usable_threads"]
+    return max(1, u // info["threads_per_core"] if u >= 16 else u)
+
+
+def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int, seed: int, warm_frames: int = 100):
+    """n_procs independent reference processes, each loading the model once and decoding one short warm-up
+    utterance followed by n_timed utterances of n_frames frames.  Returns per-process
+    (timed frames, timed decode seconds); decode time = between PASS1_BEGIN and PASS1_END of each utterance."""
+    from julius_b200 import workload
     jref = os.path.join(ROOT, "oracle", "_ref", "jref")
     if not os.path.exists(jref):
         raise RuntimeError("oracle/_ref/jref is missing (built by __graft_entry__.build() where /root/reference exists)")
@@ -122,73 +179,109 @@ def run_reference_sample(workload_name: str, n_procs: int, utts_per_proc: int, n
     tmp = tempfile.mkdtemp(prefix="jb200_ref_")
     rng = np.random.default_rng(seed)
     procs = []
-    env = dict(os.environ, JREF_QUIET="1")
+    env = dict(os.environ, JREF_QUIET="1", JREF_PER_UTT="1")
     for pi in range(n_procs):
         files = []
-        for ui in range(utts_per_proc):
+        for ui in range(n_timed + 1):
             fn = os.path.join(tmp, f"p{pi}_u{ui}.mfc")
-            x = workload.sample_inputs(workload_name, m, 1, n_frames, seed=int(rng.integers(1 << 30)))[0]
+            x = workload.sample_inputs(workload_name, m, 1, warm_frames if ui == 0 else n_frames, seed=int(rng.integers(1 << 30)))[0]
             workload.write_input(workload_name, fn, x)
             files.append(fn)
-        args = [jref, "-dump", os.path.join(tmp, f"p{pi}.jrf")] + workload.ref_args(workload_name)
+        args = [jref, "-dump", "/dev/null"] + workload.ref_args(workload_name)
         p = subprocess.Popen(args, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
         p.stdin.write("\n".join(files) + "\n")
         p.stdin.close()
         procs.append(p)
-    secs, frames = [], 0
+    per_proc = []
     for p in procs:
         out = p.stdout.read()
         p.wait()
+        fr, sec = 0, 0.0
         for line in out.splitlines():
-            if line.startswith("JREF_SUMMARY"):
+            if line.startswith("JREF_UTT"):
                 kv = dict(x.split("=") for x in line.split()[1:])
-                secs.append(float(kv["decode_sec"])); frames += int(kv["frames"])
+                if int(kv["idx"]) >= 1:                   # idx 0 is the warm-up utterance
+                    fr += int(kv["frames"]); sec += float(kv["decode_sec"])
+        if fr:
+            per_proc.append((fr, sec))
     for f in os.listdir(tmp):
         os.remove(os.path.join(tmp, f))
     os.rmdir(tmp)
-    if not secs:
-        raise RuntimeError("reference produced no summary")
-    return frames, max(secs)
+    if not per_proc:
+        raise RuntimeError("reference produced no timing lines")
+    return per_proc
 
 
-def ref_procs() -> int:
-    """One reference process per physical core: the decoder is single-threaded and memory-bound, so
-    running one per hardware thread is slower in aggregate (measured on the B200 box: 64 processes
-    6.2k frames/s, 128 processes 3.5k frames/s).  JB200_REF_PROCS overrides."""
-    if os.environ.get("JB200_REF_PROCS"):
-        return max(1, int(os.environ["JB200_REF_PROCS"]))
-    cores = os.cpu_count() or 1
-    return max(1, cores // 2 if cores >= 16 else cores)
+def reference_measure(workload_name: str, n_timed: int, n_frames: int, seed: int) -> dict:
+    """The reference CPU arm, sized to the cores this process may use.  A 1-process probe gives the uncontended
+    per-process rate; if the per-process rate of the full run falls below half of it the cores are oversubscribed
+    (a CPU-restricted lease that affinity/cgroup do not show) and the process count is halved and the run repeated."""
+    info = host_cpus()
+    n = ref_procs(info)
+    probe = run_reference(workload_name, 1, 1, min(n_frames, 300), seed + 7)
+    probe_rate = probe[0][0] / probe[0][1]
+    tried = []
+    while True:
+        pp = run_reference(workload_name, n, n_timed, n_frames, seed)
+        frames = sum(f for f, _ in pp)
+        slowest = max(s for _, s in pp)
+        rates = [f / s for f, s in pp]
+        per_proc = float(np.median(rates))
+        tried.append({"nproc": n, "frames_per_s": frames / slowest, "frames_per_s_per_process": per_proc})
+        if per_proc >= 0.5 * probe_rate or n == 1 or len(tried) >= 4 or os.environ.get("JB200_REF_PROCS"):
+            break
+        n = max(1, n // 2)
+    best = max(tried, key=lambda r: r["frames_per_s"])
+    last = tried[-1]
+    # report the configuration with the highest aggregate rate among those tried (the reference's best showing)
+    return {"value": best["frames_per_s"], "nproc": best["nproc"], "frames_per_s_per_process": best["frames_per_s_per_process"],
+            "probe_frames_per_s_1proc": probe_rate, "oversubscribed": bool(last["frames_per_s_per_process"] < 0.5 * probe_rate),
+            "tried": tried, "timed_sec_slowest_process": (n_timed * n_frames * best["nproc"]) / best["frames_per_s"],
+            "cpu_count": info["cpu_count"], "affinity": info["affinity"], "cgroup_quota": info["cgroup_quota"],
+            "threads_per_core": info["threads_per_core"]}
 
 
 def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_procs = ref_procs()
     upp = a.cpu_sample_utts or 1
-    # steps are bounded samples of the same workload
-    for w in range(min(a.warmup, 1)):
-        run_reference_sample(a.workload, n_procs, 1, min(a.frames, 200), 900 + w)
-    tot_f, tot_s = 0, 0.0
-    for k in range(a.steps):
-        f, s = run_reference_sample(a.workload, n_procs, upp, a.frames, 1000 + k)
-        tot_f += f; tot_s += s
-    v = tot_f / tot_s
+    n_timed = a.steps * upp
+    r = reference_measure(a.workload, n_timed, a.frames, 1000)
+    v = r["value"]
+    sample = (f"{r['nproc']} independent reference processes (one per usable physical core; affinity {r['affinity']}, "
+              f"cgroup quota {r['cgroup_quota']}, cpu_count {r['cpu_count']}), each loads the model once, decodes a 100-frame warm-up "
+              f"utterance and then {a.steps} steps x {upp} utterances x {a.frames} frames; decode time between PASS1_BEGIN/END, "
+              f"slowest process; {r['frames_per_s_per_process']:.0f} frames/s per process (1-process probe {r['probe_frames_per_s_1proc']:.0f})")
     line = {
         "impl": "reference", "metric": "frames/sec (xRT) 20k-word triphone decode", "value": v, "unit": "frames/s",
         "xRT": v / 100.0, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1000.0 * tot_s / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1000.0 * r["timed_sec_slowest_process"] / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{a.workload}: tied-state triphone GMM 3000x16x39, 20k-word 2-gram, beam 800, -1pass; "
-                               f"{n_procs} independent reference processes x {upp} utterances x {a.frames} frames per step"},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": n_procs, "kind": "reference",
-                         "sample": f"{a.steps} steps x {n_procs} procs x {upp} utts x {a.frames} frames; decode time between PASS1_BEGIN/END, max over processes"},
+        "config": {"workload": workload_label(a.workload), "utts_per_step": r["nproc"] * upp, "frames_per_utt": a.frames,
+                   "parallelism": f"{r['nproc']} independent single-threaded reference processes on the host cores"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": r["nproc"], "kind": "reference", "sample": sample,
+                         **{k: r[k] for k in ("nproc", "cpu_count", "affinity", "cgroup_quota", "frames_per_s_per_process",
+                                              "probe_frames_per_s_1proc", "oversubscribed", "tried")}},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+WORKLOAD_LABELS = {
+    "tri20k": "tri20k: tied-state triphone GMM 3000 states x 16 mix x 39 dim, 20k-word 2-gram (BASELINE configs[1]), beam 800, pass 1",
+    "tri20k_gbeam": "tri20k_gbeam: the same triphone GMM with -gprune beam (BASELINE configs[2]), 20k-word 2-gram, beam 800, pass 1",
+    "tri20k_mp": "tri20k_mp: the triphone GMM on the multipath tree (-multipath), 20k-word 2-gram, beam 800, pass 1",
+    "dnn20k": "dnn20k: DNN-HMM 528 -> 7 x 2048 logistic -> 3000 states (BASELINE configs[3] shape), 20k-word 2-gram, beam 800, pass 1",
+    "dnn60k_mp": "dnn60k_mp: DNN-HMM 528 -> 7 x 2048 -> 3000 states, 60k-word multipath tree, -iwsp -iwcd1 max -b 4000 (BASELINE configs[4]), pass 1",
+    "mono100": "mono100: monophone GMM 16 mix x 39 dim, 100-word grammar (BASELINE configs[0])",
+}
+
+
+def workload_label(name: str) -> str:
+    return WORKLOAD_LABELS.get(name, name)
 
 
 # --------------------------------------------------------------------------------------- product arm
@@ -240,9 +333,9 @@ def product_main(a):
     off = np.arange(B + 1, dtype=np.int32) * T
     host_batches, dev_batches = [], []
     for bi in range(n_batches):
-        # a pool of 32 sampled utterances tiled to B (sampling 592k frames in numpy is the slow part)
-        pool = workload.sample_inputs(a.workload, m, min(B, 32), T, seed=100 + 17 * rank + bi)
-        feats = np.concatenate([pool[i % len(pool)] for i in range(B)], 0)
+        # B DISTINCT utterances per batch (no tiling: identical blocks would walk the same tree nodes, bigram rows and
+        # memo entries in step and flatter the cache hit rates); ~17 ms of numpy per utterance
+        feats = np.concatenate(workload.sample_inputs(a.workload, m, B, T, seed=100 + 17 * rank + 1000 * bi), 0)
         hb = torch.from_numpy(feats).pin_memory()
         host_batches.append(hb)
         dev_batches.append(hb.to(device))
@@ -336,14 +429,18 @@ def product_main(a):
             dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
         ach = dom_bytes / (dom_ms / 1000.0) / 1e9
         # DRAM traffic of the dominant kernel per launch, scaled from the committed ncu --set full capture
-        traffic = None
+        traffic, traffic_note = None, "no ncu capture of this kernel build under profiles/"
         tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tfile):
             tj = json.load(open(tfile))
-            if dom == "beam_kernel" and "beam_kernel" in tj:
-                traffic = tj["beam_kernel"]["bytes_per_utterance_frame"] * B * T
-            elif dom == "gmm_score_kernel" and "gmm_score_kernel" in tj:
-                traffic = tj["gmm_score_kernel"]["bytes_per_frame"] * B * T
+            ent = tj.get(dom)
+            if ent is not None and ent.get("source_sha") != kernel_source_sha():
+                traffic_note = (f"profiles/ncu_traffic.json was captured from another build of {dom} "
+                                f"(source_sha {ent.get('source_sha')} != {kernel_source_sha()}): not reported")
+            elif ent is not None:
+                per = ent.get("bytes_per_utterance_frame", ent.get("bytes_per_frame"))
+                traffic = per * B * T
+                traffic_note = f"ncu dram read+write of this build ({ent.get('capture')}), per utterance-frame x {B * T} utterance-frames"
         tensor = None
         if use_dnn:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -367,7 +464,7 @@ def product_main(a):
                        "l2": "per-step working set (score matrix %.1f GB) exceeds L2; input batch alternates" % (B * T * S * 4 / 1e9),
                        "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, scaled from profiles/ncu_traffic.json)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_note": traffic_note,
                          "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
                          "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
                          "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
@@ -383,12 +480,13 @@ def product_main(a):
         }
         if world == 1 and not a.no_cpu_baseline:
             try:
-                n_procs = ref_procs()
                 upp = a.cpu_sample_utts or 1
-                f, s = run_reference_sample(a.workload, n_procs, upp, T, 4242)
-                line["cpu_baseline"] = {"value": f / s, "unit": "frames/s", "cores": n_procs, "kind": "reference",
-                                        "sample": f"{n_procs} reference processes x {upp} utterances x {T} frames of the same workload; "
-                                                  f"decode time between PASS1_BEGIN/END, max over processes ({s:.1f} s)"}
+                r = reference_measure(a.workload, upp, T, 4242)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["nproc"], "kind": "reference",
+                                        "sample": f"{r['nproc']} reference processes (one per usable physical core) x {upp} utterances x {T} frames of the "
+                                                  f"same workload after a 100-frame warm-up utterance; decode time between PASS1_BEGIN/END, slowest process",
+                                        **{k: r[k] for k in ("nproc", "cpu_count", "affinity", "cgroup_quota", "frames_per_s_per_process",
+                                                             "probe_frames_per_s_1proc", "oversubscribed")}}
             except Exception as e:   # the bench line must still print
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))

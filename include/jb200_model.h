@@ -238,27 +238,47 @@ static inline int jb200_blob_save(const jb200_blob *b, const char *path) {
   return 0;
 }
 
+/* Reads a blob file.  The file is not trusted: dtype must be one of the three known types, every count must fit in
+ * what is left of the file, allocations are checked.  On any error the blob is left empty and a negative code is
+ * returned (-1 cannot open, -2 not a JB2M v1 file, -3 truncated or inconsistent, -4 out of memory). */
 static inline int jb200_blob_load(jb200_blob *b, const char *path) {
   FILE *fp = fopen(path, "rb");
-  char magic[4]; int32_t hdr[3]; int i;
+  char magic[4]; int32_t hdr[3]; int i, rc = 0;
+  long fsize, pos;
   jb200_blob_init(b);
   if (!fp) return -1;
+  if (fseek(fp, 0, SEEK_END) != 0 || (fsize = ftell(fp)) < 0 || fseek(fp, 0, SEEK_SET) != 0) { fclose(fp); return -3; }
   if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, "JB2M", 4) != 0) { fclose(fp); return -2; }
   if (fread(hdr, 4, 3, fp) != 3 || hdr[0] != 1) { fclose(fp); return -2; }
-  b->cap = b->n = hdr[1];
-  b->e = (jb200_blob_entry *)calloc((size_t)b->n, sizeof(jb200_blob_entry));
-  for (i = 0; i < b->n; i++) {
+  if (hdr[1] < 0 || (long)hdr[1] > (fsize - 16) / 64) { fclose(fp); return -3; }       /* an entry header is 64 bytes */
+  b->e = (jb200_blob_entry *)calloc((size_t)(hdr[1] > 0 ? hdr[1] : 1), sizeof(jb200_blob_entry));
+  if (!b->e) { fclose(fp); return -4; }
+  b->cap = hdr[1];
+  for (i = 0; i < hdr[1] && rc == 0; i++) {
     jb200_blob_entry *x = &b->e[i];
     int32_t dt[2]; size_t nbytes;
-    if (fread(x->name, 1, 48, fp) != 48 || fread(dt, 4, 2, fp) != 2 || fread(&x->count, 8, 1, fp) != 1) { fclose(fp); return -3; }
+    if (fread(x->name, 1, 48, fp) != 48 || fread(dt, 4, 2, fp) != 2 || fread(&x->count, 8, 1, fp) != 1) { rc = -3; break; }
+    x->name[47] = '\0';
     x->dtype = dt[0];
+    pos = ftell(fp);
+    if (x->dtype != JB200_F32 && x->dtype != JB200_I32 && x->dtype != JB200_U8) { rc = -3; break; }
+    if (pos < 0 || x->count < 0 || x->count > (int64_t)(fsize - pos) / (int64_t)jb200_dtype_size(x->dtype)) { rc = -3; break; }
     nbytes = (size_t)x->count * jb200_dtype_size(x->dtype);
     x->data = malloc(nbytes ? nbytes : 1);
-    if (nbytes && fread(x->data, 1, nbytes, fp) != nbytes) { fclose(fp); return -3; }
+    if (!x->data) { rc = -4; break; }
+    b->n = i + 1;                                   /* x->data is owned by the blob from here on */
+    if (nbytes && fread(x->data, 1, nbytes, fp) != nbytes) { rc = -3; break; }
     if (nbytes % 16) fseek(fp, (long)(16 - nbytes % 16), SEEK_CUR);
   }
   fclose(fp);
-  return 0;
+  if (rc != 0) jb200_blob_free(b);
+  return rc;
+}
+
+/* 1 when the entry exists with the given type and at least `need` elements */
+static inline int jb200_blob_has(const jb200_blob *b, const char *name, int dtype, int64_t need) {
+  const jb200_blob_entry *x = jb200_blob_find(b, name);
+  return x != NULL && x->dtype == dtype && need >= 0 && x->count >= need;
 }
 
 /* typed getters: return NULL / default when missing */
@@ -299,6 +319,15 @@ static inline int jb200_gmm_from_blob(const jb200_blob *b, jb200_gmm_desc *g) {
   g->valid = (const uint8_t *)jb200_blob_ptr(b, "gmm.valid", NULL);
   g->cd_off = (const int32_t *)jb200_blob_ptr(b, "am.cd_off", NULL);
   g->cd_states = (const int32_t *)jb200_blob_ptr(b, "am.cd_states", NULL);
+  /* every array must be as long as the declared dimensions say */
+  if (g->n_states < 0 || g->dim < 1 || g->n_gauss < 0 || g->n_cdsets < 0 || g->n_cdset_states < 0) return -1;
+  if (!jb200_blob_has(b, "gmm.state_off", JB200_I32, (int64_t)g->n_states + 1) ||
+      !jb200_blob_has(b, "gmm.mean", JB200_F32, (int64_t)g->n_gauss * g->dim) ||
+      !jb200_blob_has(b, "gmm.ivar", JB200_F32, (int64_t)g->n_gauss * g->dim) ||
+      !jb200_blob_has(b, "gmm.gconst", JB200_F32, g->n_gauss) || !jb200_blob_has(b, "gmm.lnweight", JB200_F32, g->n_gauss) ||
+      !jb200_blob_has(b, "gmm.valid", JB200_U8, g->n_gauss)) return -1;
+  if (g->n_cdsets > 0 && (!jb200_blob_has(b, "am.cd_off", JB200_I32, (int64_t)g->n_cdsets + 1) ||
+                          !jb200_blob_has(b, "am.cd_states", JB200_I32, g->n_cdset_states))) return -1;
   return 0;
 }
 
@@ -309,13 +338,18 @@ static inline int jb200_dnn_from_blob(const jb200_blob *b, jb200_dnn_desc *d) {
   d->n_layers = jb200_blob_get_i(b, "dnn.n_layers", 0);
   d->in_dim = jb200_blob_get_i(b, "dnn.in_dim", 0);
   d->out_dim = jb200_blob_get_i(b, "dnn.out_dim", 0);
-  for (i = 0; i < d->n_layers && i < JB200_DNN_MAX_LAYERS; i++) {
+  if (d->n_layers < 1 || d->n_layers > JB200_DNN_MAX_LAYERS || d->in_dim < 1 || d->out_dim < 1) return -1;   /* no silent truncation */
+  for (i = 0; i < d->n_layers; i++) {
     snprintf(nm, sizeof(nm), "dnn.l%d.in", i);  d->layer_in[i] = jb200_blob_get_i(b, nm, 0);
     snprintf(nm, sizeof(nm), "dnn.l%d.out", i); d->layer_out[i] = jb200_blob_get_i(b, nm, 0);
     snprintf(nm, sizeof(nm), "dnn.l%d.w", i);   d->w[i] = (const float *)jb200_blob_ptr(b, nm, NULL);
     snprintf(nm, sizeof(nm), "dnn.l%d.b", i);   d->b[i] = (const float *)jb200_blob_ptr(b, nm, NULL);
+    if (d->layer_in[i] < 1 || d->layer_out[i] < 1 || !jb200_blob_has(b, nm, JB200_F32, d->layer_out[i])) return -1;
+    snprintf(nm, sizeof(nm), "dnn.l%d.w", i);
+    if (!jb200_blob_has(b, nm, JB200_F32, (int64_t)d->layer_in[i] * d->layer_out[i])) return -1;
   }
   d->state_prior = (const float *)jb200_blob_ptr(b, "dnn.state_prior", NULL);
+  if (!jb200_blob_has(b, "dnn.state_prior", JB200_F32, d->out_dim)) return -1;
   return 0;
 }
 
@@ -345,6 +379,31 @@ static inline int jb200_tree_from_blob(const jb200_blob *b, jb200_tree_desc *t) 
 #undef JB200_GI
 #undef JB200_GF
 #undef JB200_GP
+  /* every array must be as long as the declared dimensions say (the decoder indexes them without further checks) */
+  if (t->n_nodes < 1 || t->n_arcs < 0 || t->n_words < 1 || t->n_iso < 0 || t->n_shared < 0 || t->n_fscore < 0 ||
+      t->n_scword < 0 || t->n_rset < 0 || t->n_ctx < 0 || t->lm_nvocab < 0 || t->lm_nbigram < 0 || t->n_init < 0) return -1;
+#define JB200_NEED(f, dt, cnt) if (!jb200_blob_has(b, "tree." #f, dt, (int64_t)(cnt))) return -1
+  JB200_NEED(self_a, JB200_F32, t->n_nodes); JB200_NEED(next_a, JB200_F32, t->n_nodes);
+  JB200_NEED(arc_off, JB200_I32, (int64_t)t->n_nodes + 1); JB200_NEED(arc_to, JB200_I32, t->n_arcs); JB200_NEED(arc_a, JB200_F32, t->n_arcs);
+  JB200_NEED(stend, JB200_I32, t->n_nodes); JB200_NEED(scid, JB200_I32, t->n_nodes);
+  JB200_NEED(outstyle, JB200_U8, t->n_nodes); JB200_NEED(out_ref, JB200_I32, t->n_nodes);
+  JB200_NEED(rset_ctx, JB200_I32, (int64_t)t->n_rset * (t->n_ctx + 1)); JB200_NEED(word_ctx, JB200_I32, t->n_words);
+  JB200_NEED(iso_node, JB200_I32, t->n_iso); JB200_NEED(iso_word, JB200_I32, t->n_iso); JB200_NEED(iso_id, JB200_I32, t->n_iso);
+  JB200_NEED(shared_node, JB200_I32, t->n_shared);
+  JB200_NEED(wordend_a, JB200_F32, t->n_words); JB200_NEED(wordend, JB200_I32, t->n_words); JB200_NEED(wordbegin, JB200_I32, t->n_words);
+  JB200_NEED(is_transparent, JB200_U8, t->n_words); JB200_NEED(wton, JB200_I32, t->n_words); JB200_NEED(cprob, JB200_F32, t->n_words);
+  JB200_NEED(fscore, JB200_F32, t->n_fscore); JB200_NEED(scword, JB200_I32, t->n_scword);
+  if (t->lm_type == JB200_LM_NGRAM) {
+    JB200_NEED(uni_prob, JB200_F32, t->lm_nvocab); JB200_NEED(uni_bow, JB200_F32, t->lm_nvocab);
+    JB200_NEED(bi_bgn, JB200_I32, t->lm_nvocab); JB200_NEED(bi_num, JB200_I32, t->lm_nvocab);
+    JB200_NEED(bi_wid, JB200_I32, t->lm_nbigram); JB200_NEED(bi_prob, JB200_F32, t->lm_nbigram);
+  } else {
+    JB200_NEED(init_word, JB200_I32, t->n_init); JB200_NEED(init_node, JB200_I32, t->n_init); JB200_NEED(init_lscore, JB200_F32, t->n_init);
+    JB200_NEED(cp_allowed, JB200_U8, (int64_t)t->n_words * t->n_iso);
+  }
+#undef JB200_NEED
+  if (t->lm_type == JB200_LM_NGRAM &&
+      (t->head_silwid < 0 || t->head_silwid >= t->n_words || t->tail_silwid < 0 || t->tail_silwid >= t->n_words)) return -1;
   return 0;
 }
 

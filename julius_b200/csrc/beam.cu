@@ -5,7 +5,7 @@
 // (factoring_sub.c:942-1143, ngram_access.c:249-305) and the word-trellis store/sort
 // (backtrellis.c:190-267,438-478), stock "fast" switches: N-gram LMs on normal trees (beam_kernel, body in
 // beam_frames.inc) and multipath trees (beam_kernel_mp); DFA grammars on the category tree (beam_kernel_grammar = the
-// same body with the three grammar-mode differences compiled in; opt-in until it has run against the oracle on a device).
+// same body with the three grammar-mode differences compiled in).
 //
 // Why this is not a transliteration.  The reference walks the survivors of frame t-1 one by one
 // and lets each arc "propagate" into a per-node slot; ties are won by whoever arrived first, new
@@ -32,6 +32,7 @@
 //
 // Compiled with --fmad=false: every float decision uses the reference's fp32 expression order.
 #include "common.cuh"
+#include "heap_pipe.cuh"
 #include <vector>
 #include <algorithm>
 
@@ -103,8 +104,7 @@ struct BeamParams {
   jb200_utt_result *results; int *words;
   long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
   unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
-  unsigned long long *outv;          // per-utterance extracted heap roots [beam+1]
-  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine;
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine, heap_single;
   unsigned long long *lmc; int lmc_bits;      // memo of max_successor_prob, 2^lmc_bits entries (0 = off)
   int maxt, maxc, maxw, maxbits;
   // grammar (DFA) mode, appended so that the offsets of everything above stay what the N-gram kernels were built with
@@ -429,8 +429,22 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
 template <bool MAXHEAP>
 __device__ void heap_extract_fast(unsigned long long *A, const int n, const int extract, const float lose_below,
                                   unsigned long long *outv, const int maxt, unsigned long long *stats,
-                                  const SlotClear *idle_work = nullptr) {
+                                  const SlotClear *idle_work = nullptr, const int single_thread = 0) {
   if (threadIdx.x >= 32 && idle_work) idle_work->run((int)threadIdx.x - 32, BEAM_THREADS - 32);
+  if (single_thread != 1) {
+    // warp 0: up to 16 extractions in flight, one tree level per tick each (heap_pipe.cuh)
+    if (threadIdx.x < 32) {
+      unsigned ticks, stalls;
+      if (single_thread == 2) heap_extract_pipe_warp<MAXHEAP>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
+      else heap_extract_pipe_warp4<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
+      if (threadIdx.x == 0) {
+        atomicAdd(stats + 1, (unsigned long long)ticks); atomicAdd(stats + 2, (unsigned long long)extract);
+        atomicAdd(stats + 3, (unsigned long long)stalls);
+      }
+    }
+    __syncthreads();
+    return;
+  }
   if (threadIdx.x == 0) {
     unsigned levels = 0, sink = 0, sinkacc = 0;
     const unsigned hb = smem_u32(A);
@@ -637,14 +651,14 @@ extern __shared__ __align__(16) unsigned char beam_smem[];
 // "exists") and bestkey = (score, seq 0), so later arrivals only replace its content when strictly better.
 template <bool MAXHEAP>
 __device__ __forceinline__ int select_exact(unsigned long long *heap, int n, int need, int *ordn, unsigned long long *outv, int maxt,
-                                            unsigned long long *stats) {
+                                            unsigned long long *stats, const int heap_single) {
   // sort_token_no_order (beam.c:1492-1520) replayed in full; the extracted roots are put back into the
   // tail slots where the in-place algorithm leaves them (k-th extracted at slot n-k).  Returns the first
   // survivor's slot.
   const int extract = MAXHEAP ? need : n - need;
   heap_pad_sentinels<MAXHEAP>(heap, n, maxt);
   heap_build<MAXHEAP>(heap, n);
-  heap_extract_fast<MAXHEAP>(heap, n, extract, -INFINITY, outv, maxt, stats);
+  heap_extract_fast<MAXHEAP>(heap, n, extract, -INFINITY, outv, maxt, stats, nullptr, heap_single);
   for (int k = threadIdx.x; k < extract; k += BEAM_THREADS) heap[n - k] = outv[k];
   __syncthreads();
   const int start = MAXHEAP ? n - need : 0;
@@ -680,7 +694,7 @@ beam_kernel_mp(const BeamParams p) {
   WEnd *wend = p.wend + (size_t)u * MAXW;
   unsigned *bits = p.bitmask + (size_t)u * (p.maxbits >> 5);
   int *wpre = p.wordpre + (size_t)u * (p.maxbits >> 5);
-  unsigned long long *outv = p.outv + (size_t)u * (p.beam + 1);
+  unsigned long long *outv = reinterpret_cast<unsigned long long *>(offs);   // [beam+1] extracted roots; offs is dead during the selects
   const long long a0 = p.atom_off[u];
   const int atom_cap = (int)(p.atom_off[u + 1] - a0);
   jb200_atom *araw = p.atoms_raw + a0;
@@ -853,8 +867,8 @@ beam_kernel_mp(const BeamParams p) {
         for (int k = tid; k < ns_a; k += BEAM_THREADS) ordn[k] = k;
       } else {
         ns_a = need;
-        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter);
-        else select_exact<false>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter);
+        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single);
+        else select_exact<false>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single);
       }
     }
     __syncthreads();
@@ -1123,7 +1137,7 @@ beam_kernel_mp(const BeamParams p) {
         heap_build<true>(heap, ncre); PROF_MARK(7);
         const SlotClear sc{tn, ncre, slots};
         slots_clean = true;
-        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, &sc);
+        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, &sc, p.heap_single);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
       } else {
         ns_new = need;
@@ -1131,7 +1145,7 @@ beam_kernel_mp(const BeamParams p) {
         heap_build<false>(heap, ncre); PROF_MARK(7);
         const SlotClear sc{tn, ncre, slots};
         slots_clean = true;
-        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter, &sc);
+        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter, &sc, p.heap_single);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
       }
     }
@@ -1249,11 +1263,6 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   const bool grammar = (t->lm_type == JB200_LM_DFA);
   if (t->lm_type != JB200_LM_NGRAM && !grammar) { set_error("unknown language-model type %d", t->lm_type); return JB200_ERR_UNSUPPORTED; }
   if (grammar) {
-    // beam_kernel_grammar is written against the pinned oracle but has not run on a device yet: opt-in only
-    if (!getenv("JB200_ENABLE_GRAMMAR") || atoi(getenv("JB200_ENABLE_GRAMMAR")) == 0) {
-      set_error("grammar (DFA) lexicon trees: the GPU kernel is not validated yet (set JB200_ENABLE_GRAMMAR=1 to try it)");
-      return JB200_ERR_UNSUPPORTED;
-    }
     if (t->multipath) { set_error("grammar mode on a multipath tree is not supported by the GPU beam"); return JB200_ERR_UNSUPPORTED; }
     if (t->n_shared != 0 || t->n_init < 1 || t->n_init > t->beam_width || !t->cp_allowed || !t->init_node || !t->init_lscore) {
       set_error("grammar mode: inconsistent descriptor (n_shared %d, n_init %d, beam %d)", t->n_shared, t->n_init, t->beam_width);
@@ -1263,6 +1272,11 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
       if (t->is_transparent[i]) { set_error("grammar mode: transparent words are not supported"); return JB200_ERR_UNSUPPORTED; }
   }
   if (t->n_nodes >= (1 << 28)) { set_error("lexicon tree too large"); return JB200_ERR_UNSUPPORTED; }
+  // a transparent head silence would end the first word with no context word at all (last_word = -1): the reference
+  // indexes wton[] / the inter-word cache with WORD_INVALID there (factoring_sub.c:1052-1056), i.e. has no defined result
+  if (!grammar && (t->head_silwid < 0 || t->head_silwid >= t->n_words || t->is_transparent[t->head_silwid])) {
+    set_error("the head silence word must exist and must not be transparent"); return JB200_ERR_UNSUPPORTED;
+  }
   if (t->beam_width < 1 || t->beam_width > 8000) { set_error("beam width %d outside 1..8000", t->beam_width); return JB200_ERR_UNSUPPORTED; }
   jb200_decoder *d = new jb200_decoder();
   d->am = am; d->device = gmm_device(am); d->dim = gmm_dim(am);
@@ -1401,7 +1415,6 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.maxbits = (P.maxc + std::min(P.maxw, 256) * n_isoent + std::max(t->n_shared, P.n_sharc) + 63) & ~31;
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.bitmask));
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.wordpre));
-  TRY(dev_alloc(d, (size_t)max_utts * (t->beam_width + 1), &P.outv));
   TRY(dev_alloc(d, 4, &P.misspec_counter));        // [0] mis-speculations, [1] sift levels, [2] extractions
   TRYC(cudaMemset(P.misspec_counter, 0, 4 * sizeof(unsigned long long)));
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
@@ -1419,6 +1432,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   }
   P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
+  P.heap_single = getenv("JB200_HEAP_SINGLE") ? atoi(getenv("JB200_HEAP_SINGLE")) : 0;   // 1: the single-thread replay, 2: the branchy pipelined loop (A/B timing)
   {
     size_t tot = (size_t)max_utts * n;
     fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.slots, tot);

@@ -4,17 +4,21 @@
  * libjulius/include/julius/extern.h:56-61).  Linking libjulius with this object INSTEAD of beam.o
  * turns the stock Julius host into a front for the GPU path, jconf surface unchanged:
  *
- *   get_back_trellis_init(param, r)      beam.c:1825  buffered input: param holds all T frames, so the
- *                                                    whole utterance is scored and decoded on the GPU now
- *                                                    (jb200_decode_batch_host); bt_prepare as the original
- *   get_back_trellis_proceed(t, ...)     beam.c:2663  nothing left to do per frame; returns TRUE
- *   get_back_trellis_end(param, r)       beam.c:3052  materialises r->backtrellis from the GPU's atoms
- *                                                    through bt_new/bt_store (backtrellis.c:154,190)
+ *   get_back_trellis_init(param, r)      beam.c:1825  bt_prepare and the per-utterance host state, as the original
+ *   get_back_trellis_proceed(t, ...)     beam.c:2663  nothing to do per frame; returns TRUE, no interim result
+ *   get_back_trellis_end(param, r)       beam.c:3052  param now holds ALL frames of the input in both of the host's
+ *                                                    modes -- buffered (pass1.c:220-254 calls _init with the whole
+ *                                                    utterance) and real-time (realtime-1stpass.c:681 calls _init with
+ *                                                    ONE frame and grows param as audio arrives) -- so this is where
+ *                                                    the utterance is scored and decoded on the GPU
+ *                                                    (jb200_decode_batch_host) and r->backtrellis is materialised from
+ *                                                    the GPU's atoms through bt_new/bt_store (backtrellis.c:154,190)
  *   finalize_1st_pass(r, len)            beam.c:3133  bt_relocate_rw + bt_sort_rw, then publishes the
  *                                                    pass-1 best exactly where find_1pass_result does
  *                                                    (beam.c:497-512)
  *   fsbeam_free(d)                       beam.c:3180
- * Restrictions (checked, fail loudly): N-gram LM, no short-pause segmentation, buffered input
+ * Restrictions (checked, fail loudly): N-gram LM, no short-pause segmentation, feature-vector input at least as wide
+ * as the model's.  Progressive (interim) output is not produced: pass 1 runs when the input is complete.
  * (normal and multipath trees both run on the device).  The models are flattened on first use with the same code as the plugin.
  */
 #include <julius/juliuslib.h>
@@ -75,19 +79,25 @@ static Shim *shim_for(RecogProcess *r, int frames) {
     g_nshim++;
     jlog("STAT: jb200: GPU pass-1 beam attached to %02d %s\n", r->config->id, r->config->name);
   }
-  /* (re)create the decoder for the longest utterance seen so far */
-  s->max_frames = frames < 4096 ? 4096 : frames + frames / 2;
-  rc = g_api.decoder_create(&s->td, s->gmm, 1, s->max_frames, &s->dec);
-  if (rc == 0 && s->dnn) rc = g_api.decoder_attach_dnn(s->dec, s->dnn);
-  if (rc != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); return NULL; }
+  /* (re)create the decoder for the longest utterance seen so far: the old one (device work areas, pinned host
+   * buffers) is released first, and the capacity is recorded only once the new one exists */
+  {
+    const int want = frames < 4096 ? 4096 : frames + frames / 2;
+    if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; s->max_frames = 0; }
+    rc = g_api.decoder_create(&s->td, s->gmm, 1, want, &s->dec);
+    if (rc == 0 && s->dnn) rc = g_api.decoder_attach_dnn(s->dec, s->dnn);
+    if (rc != 0) {
+      jlog("ERROR: jb200: %s\n", g_api.last_error());
+      if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; }
+      return NULL;
+    }
+    s->max_frames = want;
+  }
   return s;
 }
 
 boolean get_back_trellis_init(HTK_Param *param, RecogProcess *r) {
   Shim *s;
-  int T = param->samplenum, D, t;
-  int32_t off[2];
-  float *in;
   bt_prepare(r->backtrellis);
   r->pass1.bos.wid = WORD_INVALID;
   r->pass1.bos.begintime = r->pass1.bos.endtime = -1;
@@ -95,17 +105,14 @@ boolean get_back_trellis_init(HTK_Param *param, RecogProcess *r) {
    * the per-node triphone caches of outprob_style (bt_discount_pescore and the stack decoder read them) */
   outprob_style_cache_init(r->wchmm);
   r->config->output.progout_interval_frame = (int)((float)r->config->output.progout_interval / ((float)param->header.wshift / 10000.0));
-  s = shim_for(r, T);
+  s = shim_for(r, 1);
   if (s == NULL) return FALSE;
   s->ok = FALSE;
   if (param->is_outprob) { jlog("ERROR: jb200: outprob-vector input is not supported by the GPU beam shim\n"); return FALSE; }
-  D = s->gd.dim;
-  in = (float *)malloc(sizeof(float) * (size_t)T * D);
-  for (t = 0; t < T; t++) memcpy(in + (size_t)t * D, param->parvec[t], sizeof(float) * D);
-  off[0] = 0; off[1] = T;
-  if (g_api.decode_batch_host(s->dec, in, off, 1) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); free(in); return FALSE; }
-  free(in);
-  s->ok = TRUE;
+  if (param->veclen < s->gd.dim) {
+    jlog("ERROR: jb200: input vectors have %d components, the acoustic model takes %d\n", (int)param->veclen, s->gd.dim);
+    return FALSE;
+  }
   return TRUE;
 }
 
@@ -117,9 +124,22 @@ boolean get_back_trellis_proceed(int t, HTK_Param *param, RecogProcess *r, boole
 void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
   const jb200_utt_result *u; const jb200_atom *a; const int32_t *w;
   TRELLIS_ATOM **idx;
-  Shim *s = shim_for(r, 0);
-  int i;
-  if (s == NULL || !s->ok) return;
+  const int T = param->samplenum;
+  Shim *s = shim_for(r, T);
+  int i, t, D;
+  int32_t off[2];
+  float *in;
+  if (s == NULL) return;
+  s->ok = FALSE;
+  if (T < 1 || param->is_outprob || param->veclen < s->gd.dim) return;       /* refused at _init already */
+  D = s->gd.dim;
+  in = (float *)malloc(sizeof(float) * (size_t)T * D);
+  if (in == NULL) { jlog("ERROR: jb200: out of memory\n"); return; }
+  for (t = 0; t < T; t++) memcpy(in + (size_t)t * D, param->parvec[t], sizeof(float) * D);
+  off[0] = 0; off[1] = T;
+  if (g_api.decode_batch_host(s->dec, in, off, 1) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); free(in); return; }
+  free(in);
+  s->ok = TRUE;
   if (g_api.decoder_results(s->dec, &u, &a, &w) != 0) return;
   if (u->overflow) { jlog("ERROR: jb200: device work area overflow (code %d); pass 1 result dropped\n", u->overflow); return; }
   a += u->atom_offset;
@@ -179,6 +199,17 @@ void finalize_1st_pass(RecogProcess *r, int len) {
 }
 
 void fsbeam_free(FSBeam *d) {
+  int i;
   if (d->pausemodelnames != NULL) { free(d->pausemodelnames); free(d->pausemodel); }
   if (d->boslist != NULL) free(d->boslist);
+  /* release the device side of the recognition instance this work area belongs to */
+  for (i = 0; i < g_nshim; i++) {
+    Shim *s = &g_shim[i];
+    if (s->r == NULL || &(s->r->pass1) != d) continue;
+    if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; }
+    if (s->dnn) { g_api.dnn_destroy(s->dnn); s->dnn = NULL; }
+    if (s->gmm) { g_api.gmm_destroy(s->gmm); s->gmm = NULL; }
+    jb200_blob_free(&s->blob);
+    s->r = NULL; s->max_frames = 0; s->ok = FALSE;
+  }
 }

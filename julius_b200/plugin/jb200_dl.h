@@ -22,6 +22,9 @@ typedef struct {
   int (*decoder_attach_dnn)(jb200_decoder *, jb200_dnn *);
   int (*decode_batch_host)(jb200_decoder *, const float *, const int32_t *, int);
   int (*decoder_results)(jb200_decoder *, const jb200_utt_result **, const jb200_atom **, const int32_t **);
+  void (*decoder_destroy)(jb200_decoder *);
+  void (*gmm_destroy)(jb200_gmm *);
+  void (*dnn_destroy)(jb200_dnn *);
 } jb200_api;
 
 static int jb200_api_load(jb200_api *a, void *anchor) {
@@ -49,6 +52,9 @@ static int jb200_api_load(jb200_api *a, void *anchor) {
   JB200_SYM(decoder_attach_dnn, "jb200_decoder_attach_dnn");
   JB200_SYM(decode_batch_host, "jb200_decode_batch_host");
   JB200_SYM(decoder_results, "jb200_decoder_results");
+  JB200_SYM(decoder_destroy, "jb200_decoder_destroy");
+  JB200_SYM(gmm_destroy, "jb200_gmm_destroy");
+  JB200_SYM(dnn_destroy, "jb200_dnn_destroy");
 #undef JB200_SYM
   return 0;
 }

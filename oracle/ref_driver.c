@@ -87,6 +87,7 @@ static void on_pass1_end(Recog *recog, void *dummy) {
   double dt = now_sec() - g_t0;
   g_decode_sec += dt;
   g_frames += T;
+  if (getenv("JREF_PER_UTT")) { fprintf(stdout, "JREF_UTT idx=%d frames=%d decode_sec=%.6f\n", g_utt, T, dt); fflush(stdout); }
 
   wi(0x4a524631); /* 'JRF1' */
   wi(g_utt++); wi(T);

@@ -222,8 +222,21 @@ static void sort_token_downward(Beam *b, int neednum, int totalnum) {
   }
 }
 
+/* test tooling: oracle_set_heap_dump(path) makes every beam cut append (totalnum, neednum, scores in token-index
+   order) to a file, so that tools/heapstat.cpp and the heap micro-benchmarks run on the selects of a real decode */
+static FILE *heap_dump_fp = NULL;
+void oracle_set_heap_dump(const char *path) {
+  if (heap_dump_fp) { fclose(heap_dump_fp); heap_dump_fp = NULL; }
+  if (path && path[0]) heap_dump_fp = fopen(path, "wb");
+}
+
 static void sort_token_no_order(Beam *b, int neednum, int *start, int *end) {
   int totalnum = b->tnum[b->tn], restnum = totalnum - neednum;
+  if (heap_dump_fp && neednum < totalnum) {
+    int hdr[2] = { totalnum, neednum }, i;
+    fwrite(hdr, sizeof(int), 2, heap_dump_fp);
+    for (i = 0; i < totalnum; i++) fwrite(&b->tlist[b->tn][b->tindex[b->tn][i]].score, sizeof(float), 1, heap_dump_fp);
+  }
   if (neednum >= totalnum) { *start = 0; *end = totalnum - 1; }
   else if (neednum < restnum) { sort_token_upward(b, neednum, totalnum); *start = totalnum - neednum; *end = totalnum - 1; }
   else { sort_token_downward(b, restnum, totalnum); *start = 0; *end = neednum - 1; }

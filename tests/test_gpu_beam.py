@@ -124,18 +124,6 @@ def test_forced_sequential_heap_gives_same_trellis(monkeypatch):
         _check(r, u)
 
 
-def test_grammar_mode_is_refused_without_opt_in(monkeypatch):
-    """tests/golden/small_dfa is a DFA-grammar model (category tree).  Its kernel (beam_kernel_grammar) is written
-    against the CPU-pinned oracle but has not been run on a device yet, so creation must fail loudly by default."""
-    monkeypatch.delenv("JB200_ENABLE_GRAMMAR", raising=False)
-    g = Golden("small_dfa")
-    am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
-    with pytest.raises(capi.Jb200Error):
-        capi.Decoder(g.ds, am, max_utts=2, max_frames=512)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("JB200_ENABLE_GRAMMAR") != "1",
-                    reason="grammar-mode kernel is opt-in (JB200_ENABLE_GRAMMAR=1) until it has been validated on a device")
 def test_grammar_mode_trellis_matches_reference():
     g = Golden("small_dfa")
     am = capi.GmmScorer(g.ds, mode=capi.GMM_EXACT)
@@ -146,8 +134,6 @@ def test_grammar_mode_trellis_matches_reference():
         _check(r, u)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("JB200_GPU_EXTRA_CASES") != "1",
-                    reason="cases pinned on the CPU only so far; JB200_GPU_EXTRA_CASES=1 runs them on the device")
 @pytest.mark.parametrize("case", ["small_tr", "small_tm"])
 def test_cpu_pinned_cases_end_to_end_on_the_device(case):
     """transparent (filler) words and the flattened tied-mixture model: host features -> GPU scores -> GPU beam."""

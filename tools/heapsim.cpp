@@ -83,6 +83,72 @@ static void kernel_select(std::vector<Ent> &A, int n, int extract, int maxt, flo
   }
 }
 
+
+// ---- the pipelined formulation (heap_extract_pipe in beam.cu) -------------------------------------------------------
+// One warp, lock-step "ticks".  Extraction x is owned by lane x mod NL; an extraction in flight moves its hole down
+// exactly one tree level per tick; a new extraction starts at the earliest two ticks after the previous one (so it reads
+// level L+1 one tick after its predecessor wrote it) and only when no extraction in flight has its hole on an ancestor
+// of (or at) the tail slot it is about to take -- such an extraction could still place its own s into that slot, and it
+// still compares against the slot's real content.  The value an extraction writes into the root is the next one's
+// output.  State is updated in the order the kernel uses inside a tick: (1) all lanes in flight read their children
+// pair, (2) they write their hole and move, (3) the start decision is taken on the holes as they are now; the starting
+// lane reads its s and retires the tail slot, and works on the root from the next tick on.
+template <bool MAXHEAP>
+static long pipelined_select(std::vector<Ent> &A, int n, int extract, int maxt, float lose_below, std::vector<Ent> &outv,
+                             int NL = 16) {
+  const float sent = MAXHEAP ? NEG : POS;
+  for (int i = n + 1; i <= std::min(2 * n + 1, maxt + 1); i++) A[i] = Ent{0, sent};
+  A[maxt + 2] = A[maxt + 3] = Ent{0, sent};
+  for (int root = n / 2; root >= 1; root--) sift_down<MAXHEAP>(A, root, n);
+  const int cap = maxt / 2 + 1;
+  struct Lane { bool act = false; int x = 0, slot = 0, cur = 0; Ent s{0, 0}; };
+  std::vector<Lane> L(NL);
+  outv.assign(extract + 1, Ent{-1, 0});
+  if (extract > 0) outv[0] = A[1];
+  int next_x = 0, wait = 0; long ticks = 0;
+  while (true) {
+    bool any = false;
+    for (auto &l : L) any |= l.act;
+    if (next_x >= extract && !any) break;
+    ticks++;
+    // (1) every extraction in flight reads the children pair of its hole
+    std::vector<Ent> rx(NL), ry(NL);
+    for (int k = 0; k < NL; k++) if (L[k].act) { rx[k] = A[2 * L[k].cur]; ry[k] = A[2 * L[k].cur + 1]; }
+    // (2) every extraction in flight fills its hole and moves one level down (or ends)
+    for (int k = 0; k < NL; k++) if (L[k].act) {
+      Lane &l = L[k];
+      const bool right = hcmp<MAXHEAP>(rx[k].v, ry[k].v);
+      const Ent c = right ? ry[k] : rx[k];
+      const bool stop = hstop<MAXHEAP>(l.s.v, c.v) || (MAXHEAP && c.v < lose_below);
+      const Ent put = stop ? l.s : c;
+      A[l.slot] = put;
+      if (l.slot == 1) outv[l.x + 1] = put;            // what goes into the root is the next extraction's output
+      if (stop) l.act = false;
+      else { const int child = 2 * l.cur + (right ? 1 : 0); l.slot = child; l.cur = std::min(child, cap); }
+    }
+    // (3) start decision on the holes as they are after this tick's move; the new extraction's first level is the
+    //     next tick's business
+    int started = -1;
+    if (--wait <= 0 && next_x < extract) {
+      const int ms = n - next_x, ln = next_x % NL;
+      bool blocked = L[ln].act;
+      // a tail slot holding a loser is never a hole and never decides anything (loser cut), and a loser stays a loser
+      const bool loser = MAXHEAP && A[ms].v < lose_below;
+      for (int k = 0; k < NL && !blocked && !loser; k++) if (L[k].act) {
+        int a = ms;
+        while (a > L[k].slot) a >>= 1;
+        if (a == L[k].slot) blocked = true;
+      }
+      if (!blocked) {
+        L[ln].s = A[ms]; A[ms] = Ent{0, sent}; L[ln].x = next_x;
+        started = ln; next_x++; wait = 2;
+      }
+    }
+    if (started >= 0) { L[started].act = true; L[started].slot = 1; L[started].cur = 1; }
+  }
+  return ticks;
+}
+
 int main(int argc, char **argv) {
   const double divisor = argc > 1 ? atof(argv[1]) : 7.0;
   const int trials = argc > 2 ? atoi(argv[2]) : 3000;
@@ -104,12 +170,22 @@ int main(int argc, char **argv) {
       reference_select<true>(R, n, extract);
       kernel_select<true>(K, n, extract, maxt, lose_below, outv);
       kernel_select<true>(K2, n, extract, maxt, NEG, outv2);           // no cut: the whole array must agree
+      { std::vector<Ent> P = base, P2 = base, po, po2;
+        pipelined_select<true>(P, n, extract, maxt, lose_below, po);
+        for (int k = 0; k < extract; k++) { checks++; if (po[k].id != R[n - k].id) { mism++; break; } }
+        pipelined_select<true>(P2, n, extract, maxt, NEG, po2, 8);
+        for (int k = 0; k < extract; k++) P2[n - k] = po2[k];
+        for (int i = 1; i <= n; i++) { checks++; if (P2[i].id != R[i].id) { mism++; break; } } }
       for (int k = 0; k < extract; k++) { checks++; if (outv[k].id != R[n - k].id) { mism++; break; } }
       for (int k = 0; k < extract; k++) K2[n - k] = outv2[k];
       for (int i = 1; i <= n; i++) { checks++; if (K2[i].id != R[i].id) { mism++; break; } }
     } else {
       reference_select<false>(R, n, extract);
       kernel_select<false>(K, n, extract, maxt, NEG, outv);
+      { std::vector<Ent> P = base, po;
+        pipelined_select<false>(P, n, extract, maxt, NEG, po);
+        for (int i = 1; i <= need; i++) { checks++; if (P[i].id != R[i].id) { mism++; break; } }
+        for (int k = 0; k < extract; k++) { checks++; if (po[k].id != R[n - k].id) { mism++; break; } } }
       for (int i = 1; i <= need; i++) { checks++; if (K[i].id != R[i].id) { mism++; break; } }
       for (int k = 0; k < extract; k++) { checks++; if (outv[k].id != R[n - k].id) { mism++; break; } }
     }

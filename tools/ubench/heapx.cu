@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
+#include "../../julius_b200/csrc/heap_pipe.cuh"
 
 #define MAXT 3328
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -30,7 +31,8 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
   return r;
 }
 
-// V: 0 = as in beam.cu; 1 = outv in shared memory; 2 = no loser-cut test; 3 = non-volatile (sinkable) load;
+// V: 9 = the pipelined warp replay of heap_pipe.cuh, readable form; 14 = the shipped form (15: without __syncwarp);
+// single-thread variants: 0 = round 1's loop; 1 = outv in shared memory; 2 = no loser-cut test; 3 = non-volatile (sinkable) load;
 //    4 = one level per loop trip (no ping-pong unroll); 5 = plain load whose result is also consumed on the
 //    exit path (ptxas must issue it ahead of the stop test); 6 = 5 + both grandchild pairs requested one level
 //    ahead (two-level speculation)
@@ -240,6 +242,21 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
   for (int i = threadIdx.x; i < MAXT + 4; i += blockDim.x) A[i] = (i >= 1 && i <= n) ? init[i] : 0xff800000ull;
   __syncthreads();
   int extract = extract_in;
+  if (V >= 9) {
+    // variant 9: the pipelined warp replay of heap_pipe.cuh (what beam.cu ships)
+    if (threadIdx.x < 32) {
+      unsigned ticks, stalls;
+      long long t0 = clock64();
+      if (V == 9) jb200::heap_extract_pipe_warp<true>(A, n, extract, lose_below, outg + (size_t)blockIdx.x * 1024, MAXT, threadIdx.x, ticks, stalls);
+      else if (V == 14) jb200::heap_extract_pipe_warp4<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else jb200::heap_extract_pipe_warp4<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      long long t1 = clock64();
+      if (threadIdx.x == 0) { res[blockIdx.x * 2] = t1 - t0; res[blockIdx.x * 2 + 1] = ticks; }
+    }
+    __syncthreads();
+    if (V >= 14) for (int i = threadIdx.x; i < extract_in; i += blockDim.x) outg[(size_t)blockIdx.x * 1024 + i] = outs[i];
+    return;
+  }
   if (threadIdx.x == 0) {
     unsigned long long *outv = (V == 1) ? outs : outg + (size_t)blockIdx.x * 1024;
     unsigned levels = 0, sink = 0, sinkacc = 0;
@@ -315,7 +332,7 @@ int main() {
   cudaMalloc(&o, sizeof(unsigned long long) * 1024 * 592); cudaMalloc(&r, sizeof(hr));
   std::vector<unsigned long long> ho(1024);
   for (int blocks : {1, 592}) {
-    for (int v = 5; v < 9; v++) {
+    for (int v : {5, 9, 14, 15}) {
       for (int rep = 0; rep < 2; rep++) {
         switch (v) {
           case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
@@ -327,6 +344,9 @@ int main() {
           case 6: k<6><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 7: k<7><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 8: k<8><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 9: k<9><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 14: k<14><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 15: k<15><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
         }
         cudaDeviceSynchronize();
       }
@@ -334,7 +354,7 @@ int main() {
       cudaMemcpy(ho.data(), o, sizeof(unsigned long long) * 1024, cudaMemcpyDeviceToHost);
       int bad = 0; for (int x = 0; x < extract; x++) if ((int)(ho[x] >> 32) != ref[x]) bad++;
       double s = 0, l = 0; for (int b = 0; b < blocks; b++) { s += (double)hr[2 * b]; l += (double)hr[2 * b + 1]; }
-      printf("blocks %3d variant %d: %.0f cycles/extraction, %.2f levels/extraction, %.1f cycles/level, order mismatches %d\n",
+      printf("blocks %3d variant %d: %.0f cycles/extraction, %.2f levels(ticks)/extraction, %.1f cycles/level(tick), order mismatches %d\n",
              blocks, v, s / blocks / extract, l / blocks / extract, s / l, bad);
     }
   }
