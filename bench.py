@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance")
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the 1-utterance / 16-utterance points and the short DNN-HMM leg")
     ap.add_argument("--cpu-sample-utts", type=int, default=0)
     return ap.parse_args()
 
@@ -163,8 +164,10 @@ def ref_procs(info: dict | None = None) -> int:
     if os.environ.get("JB200_REF_PROCS"):
         return max(1, int(os.environ["JB200_REF_PROCS"]))
     info = info or host_cpus()
-    u = info["usable_threads"]
-    return max(1, u // info["threads_per_core"] if u >= 16 else u)
+    # usable_threads = min(affinity, cgroup quota); physical cores inside the affinity mask = affinity / threads per core.
+    # A quota smaller than the mask still lets every process have a core of its own.
+    physical = max(1, info["affinity"] // info["threads_per_core"])
+    return max(1, min(info["usable_threads"], physical))
 
 
 def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int, seed: int, warm_frames: int = 100):
@@ -285,29 +288,30 @@ def workload_label(name: str) -> str:
 
 
 # --------------------------------------------------------------------------------------- product arm
-def product_main(a):
-    import torch
-    import torch.distributed as dist
-    from julius_b200 import capi, desc, refdump, workload
+def fp32_peak():
+    """FP32 SIMT peak for the GMM scoring roofline: measured by tools/ubench/ffma.cu (profiles/fp32_peak.json) when that
+    capture exists, else the nominal 148 SM x 128 lanes x 2 flop x max SM clock."""
+    p = os.path.join(ROOT, "profiles", "fp32_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["ffma_tflops"]), f"measured FFMA micro-benchmark (profiles/fp32_peak.json, {d.get('when', '')})"
+    return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 figure in MEASURED_PEAKS.json)"
+
+
+def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True, n_batches=2, seed0=100):
+    """W warm-up + K timed steps of one workload at B utterances x T frames per GPU; returns the measured figures.
+    ctx: dict(rank, local, world, device, torch, dist)."""
+    torch, dist = ctx["torch"], ctx["dist"]
+    from julius_b200 import capi, desc, workload
     from julius_b200.dist import broadcast_blob
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != a.gpus:
-        if world == 1 and a.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    if rank == 0 and not workload.ready(a.workload):
-        raise SystemExit(f"workload {a.workload} is not prepared (run __graft_entry__.build() where the reference is available)")
-    blob = refdump.load_blob(workload.path(a.workload, "model.jb2m")) if rank == 0 else None
+    rank, local, world, device = ctx["rank"], ctx["local"], ctx["world"], ctx["device"]
+    if rank == 0 and not workload.ready(name):
+        raise SystemExit(f"workload {name} is not prepared (run __graft_entry__.build() where the reference is available)")
+    blob = workload.load_model(name) if rank == 0 else None
     blob = broadcast_blob(blob, rank, world, device)
     ds = desc.Descriptors(blob)
     use_dnn = ds.dnn is not None
+    dnn = None
     if use_dnn:
         S, M_total, D = ds.n_states, 0, ds.dnn.in_dim
         am = capi.GmmScorer(ds, device=local, gmm_desc=ds.cd_only_gmm())
@@ -315,27 +319,23 @@ def product_main(a):
         dnn_flops_per_frame = 2.0 * sum(int(ds.dnn.layer_in[i]) * int(ds.dnn.layer_out[i]) for i in range(ds.dnn.n_layers))
     else:
         S, M_total, D = ds.gmm.n_states, ds.gmm.n_gauss, ds.gmm.dim
-        am = capi.GmmScorer(ds, device=local, mode=capi.GMM_EXACT if a.mode == "exact" else capi.GMM_FAST)
-    T = a.frames
-    if a.utts:
-        B = a.utts
-    else:
-        probe = capi.Decoder(ds, am, max_utts=1, max_frames=8)
-        B = max(1, probe.resident_utts())      # one resident wave of thread blocks
-        probe.close()
+        am = capi.GmmScorer(ds, device=local, mode=capi.GMM_EXACT if mode == "exact" else capi.GMM_FAST)
+    probe = capi.Decoder(ds, am, max_utts=1, max_frames=8)
+    resident = max(1, probe.resident_utts())       # one resident wave of thread blocks
+    probe.close()
+    if not B:
+        B = resident
     dec = capi.Decoder(ds, am, max_utts=B, max_frames=B * T)
     if use_dnn:
         dec.attach_dnn(dnn)
 
-    # synthetic MFCC batches sampled from the model along <s> w.. </s> paths, different per rank and step
-    m = workload.synth_model(a.workload)
-    n_batches = 2
+    # synthetic input, different per rank and batch: B DISTINCT utterances per batch (no tiling: identical blocks would
+    # walk the same tree nodes, bigram rows and memo entries in step and flatter the cache hit rates)
+    m = workload.synth_model(name)
     off = np.arange(B + 1, dtype=np.int32) * T
     host_batches, dev_batches = [], []
     for bi in range(n_batches):
-        # B DISTINCT utterances per batch (no tiling: identical blocks would walk the same tree nodes, bigram rows and
-        # memo entries in step and flatter the cache hit rates); ~17 ms of numpy per utterance
-        feats = np.concatenate(workload.sample_inputs(a.workload, m, B, T, seed=100 + 17 * rank + 1000 * bi), 0)
+        feats = np.concatenate(workload.sample_inputs(name, m, B, T, seed=seed0 + 17 * rank + 1000 * bi), 0)
         hb = torch.from_numpy(feats).pin_memory()
         host_batches.append(hb)
         dev_batches.append(hb.to(device))
@@ -358,46 +358,43 @@ def product_main(a):
         capi._check(lib.jb200_decode_batch_host(dec.handle_ptr(), C.cast(hb.data_ptr(), C.POINTER(C.c_float)), offp, B), "decode_batch_host")
 
     # ---------------- value: device-resident input ----------------
-    for w in range(a.warmup):
+    for w in range(warmup):
         step_device(w)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = capi.launch_count()
     t_wall0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # events on the decoder's own stream are what the kernels run on; bracket with device-wide syncs
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     score_ms, beam_ms = [], []
-    for k in range(a.steps):
+    for k in range(steps):
         step_device(k)
-        capi._check(lib.jb200_decoder_sync_timing(dec.handle_ptr()), "sync_timing")
+        capi._check(lib.jb200_decoder_sync_timing(dec.handle_ptr()), "sync_timing")   # CUDA events on the decoder's stream
         tm = dec.timing()
         score_ms.append(tm["score"]); beam_ms.append(tm["beam"])
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     t_wall1 = time.time()
     launches = capi.launch_count() - l0
-    dev_ms = sum(score_ms) + sum(beam_ms)          # CUDA-event time on the launching stream
+    dev_ms = sum(score_ms) + sum(beam_ms)
     barrier()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---------------- e2e: host buffers through the C-ABI ----------------
-    for w in range(max(1, min(a.warmup, 2))):
-        step_host(w)
-    barrier()
-    t2 = time.perf_counter()
-    h2d = d2h = 0
-    for k in range(a.steps):
-        step_host(k)
-        h2d += host_batches[k % n_batches].numel() * 4
-        res_bytes = dec.last_d2h_bytes()
-        d2h += res_bytes
-    torch.cuda.synchronize()
-    t3 = time.perf_counter()
-    barrier()
+    e2e_ms = h2d = d2h = 0
+    if want_e2e:
+        for w in range(max(1, min(warmup, 2))):
+            step_host(w)
+        barrier()
+        t2 = time.perf_counter()
+        for k in range(steps):
+            step_host(k)
+            h2d += host_batches[k % n_batches].numel() * 4
+            d2h += dec.last_d2h_bytes()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t2) * 1000.0
+        barrier()
 
-    # sanity: results of the last batch are sane (all utterances decoded, no overflow)
     dec._last_n = B
     res = dec.results()
     phase = dec.phase_cycles(min(B, 64)).mean(0)
@@ -405,88 +402,154 @@ def product_main(a):
     counts = dec.frame_counts(0, T)
     hs = dec.heap_stats()
 
-    # max over ranks
-    vals = torch.tensor([dev_ms, (t1 - t0) * 1000.0, (t3 - t2) * 1000.0], dtype=torch.float64, device=device)
+    vals = torch.tensor([dev_ms, (t1 - t0) * 1000.0, e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in vals.cpu()]
+    out = dict(name=name, ds=ds, use_dnn=use_dnn, B=B, T=T, S=S, M_total=M_total, D=D, resident=resident, steps=steps,
+               dev_ms=dev_ms_max, wall_ms=wall_ms_max, e2e_ms=e2e_ms_max, h2d=h2d, d2h=d2h, launches=int(launches),
+               score_ms=float(np.mean(score_ms)), beam_ms=float(np.mean(beam_ms)), clocks=clocks, phase=phase,
+               n_ok=n_ok, n_res=len(res), tokens_per_frame=float(counts[:, 1].mean()), created_per_frame=float(counts[:, 0].mean()),
+               heap=hs, misspec=dec.misspeculations(), beam_width=int(ds.tree.beam_width), multipath=int(ds.tree.multipath))
+    if use_dnn:
+        out["dnn_flops_per_frame"] = dnn_flops_per_frame
+        out["dnn_layers"] = int(ds.dnn.n_layers); out["dnn_hidden"] = int(ds.dnn.layer_out[0])
+    dec.close()
+    if dnn is not None:
+        dnn.close()
+    am.close()
+    return out
+
+
+def rooflines(r, world):
+    """roofline objects of one measured workload: the kernel with the larger share against HBM (the contract's
+    `roofline`), and the scoring kernel against the pipe that binds it (`roofline_scoring`)."""
+    B, T, S = r["B"], r["T"], r["S"]
+    peak, peak_src = peaks()
+    gmm_ms, bm_ms = r["score_ms"], r["beam_ms"]
+    gmm_bytes = r["M_total"] * ALG_GMM_BYTES_PER_GAUSS + B * T * (r["D"] * 4 + 4 * S)
+    beam_bytes = B * T * r["tokens_per_frame"] * ALG_BEAM_BYTES_PER_TOKEN
+    beam_name = "beam_kernel_mp" if r["multipath"] else "beam_kernel"
+    score_name = "dnn_gemm_persistent (x%d layers)" % r["dnn_layers"] if r["use_dnn"] else "gmm_score_kernel"
+    if bm_ms >= gmm_ms:
+        dom, dom_ms, dom_bytes = beam_name, bm_ms, beam_bytes
+    else:
+        dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
+    ach = dom_bytes / (dom_ms / 1000.0) / 1e9
+    traffic, traffic_note = None, "no ncu capture of this kernel build under profiles/"
+    tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        ent = tj.get(dom)
+        if ent is not None and ent.get("source_sha") != kernel_source_sha():
+            traffic_note = (f"profiles/ncu_traffic.json was captured from another build of {dom} "
+                            f"(source_sha {ent.get('source_sha')} != {kernel_source_sha()}): not reported")
+        elif ent is not None:
+            per = ent.get("bytes_per_utterance_frame", ent.get("bytes_per_frame"))
+            traffic = per * B * T
+            traffic_note = f"ncu dram read+write of this build ({ent.get('capture')}), per utterance-frame x {B * T} utterance-frames"
+    hs = r["heap"]
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_note": traffic_note,
+            "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
+            "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
+            "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(
+                ("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "beam_cut", "heap_build"), r["phase"])},
+            "beam_tokens_per_frame": r["tokens_per_frame"], "beam_created_per_frame": r["created_per_frame"],
+            "beam_cut": {"upward_selects": hs["upward_selects"], "closed_form": hs["closed_form"],
+                         "closed_form_frac": round(hs["closed_form"] / max(hs["upward_selects"], 1), 4),
+                         "replayed_extractions": hs["extractions"],
+                         "replay_ticks_per_extraction": round(hs["levels"] / max(hs["extractions"], 1), 3)}}
+    if r["use_dnn"]:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
+        tach = B * T * r["dnn_flops_per_frame"] / (gmm_ms / 1000.0) / 1e12
+        scoring = {"bound": "tensor", "kernel": score_name, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                   "ms": gmm_ms, "frames_per_s": B * T / (gmm_ms / 1000.0),
+                   "note": "algorithmic flops (2*in*out per layer per frame); the kernel issues 3 bf16 MMAs per product term "
+                           "(hi.hi+hi.lo+lo.hi) to meet the 1e-4 tolerance, so 1/3 of peak is the ceiling of this formulation",
+                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"}
+    else:
+        fpeak, fsrc = fp32_peak()
+        fach = B * T * r["M_total"] * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12
+        scoring = {"bound": "fp32", "kernel": score_name, "achieved": fach, "peak": fpeak, "unit": "TFLOP/s", "frac": fach / fpeak,
+                   "ms": gmm_ms, "frames_per_s": B * T / (gmm_ms / 1000.0), "hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
+                   "hbm_frac": gmm_bytes / (gmm_ms / 1000.0) / 1e9 / peak,
+                   "note": "algorithmic flops (162 per Gaussian-frame, SURVEY 8d); a parameter record is reused for 256 frames, so the "
+                           "batch kernel is FP32-issue bound, not HBM bound (ridge ~10 flop/B)",
+                   "peak_source": fsrc}
+    return roof, scoring
+
+
+def product_main(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = dict(rank=rank, local=local, world=world, device=device, torch=torch, dist=dist)
+
+    r = measure_workload(ctx, a.workload, a.utts, a.frames, a.steps, a.warmup, mode=a.mode)
+    B, T = r["B"], r["T"]
+    extra = {}
+    if world == 1 and not a.no_extra_legs:
+        # what one host thread sees: a single utterance, and a batch of 16 (the drop-in beam shim decodes one
+        # utterance per call); device-event time of scoring + beam, features resident
+        for tag, b in (("latency_1utt", 1), ("batch16", 16)):
+            q = measure_workload(ctx, a.workload, b, T, 3, 2, mode=a.mode, want_e2e=True)
+            extra[tag] = {"utterances": b, "frames_per_utt": T, "ms_device": q["dev_ms"] / q["steps"], "ms_e2e": q["e2e_ms"] / q["steps"],
+                          "frames_per_s_e2e": b * T * q["steps"] / (q["e2e_ms"] / 1000.0)}
+        # K2 on the driver's record: a short leg of the DNN-HMM workload (BASELINE configs[3]) unless it is the headline
+        if a.workload != "dnn20k":
+            from julius_b200 import workload as _w
+            if _w.ready("dnn20k"):
+                q = measure_workload(ctx, "dnn20k", a.utts or min(r["resident"], 148), T, 2, 2, want_e2e=True)
+                qroof, qscoring = rooflines(q, world)
+                extra["dnn20k"] = {"config": {"workload": workload_label("dnn20k"), "utts_per_gpu": q["B"], "frames_per_utt": T},
+                                   "value": q["B"] * T * q["steps"] / (q["wall_ms"] / 1000.0), "unit": "frames/s",
+                                   "e2e": {"value": q["B"] * T * q["steps"] / (q["e2e_ms"] / 1000.0), "unit": "frames/s",
+                                           "h2d_bytes_per_step": q["h2d"] // q["steps"], "d2h_bytes_per_step": q["d2h"] // q["steps"]},
+                                   "roofline_scoring": qscoring, "kernel_ms": qroof["kernel_ms"], "decoded_ok": f"{q['n_ok']}/{q['n_res']}"}
 
     if rank == 0:
         frames_total = world * B * T * a.steps
-        value = frames_total / (wall_ms_max / 1000.0)
-        e2e = frames_total / (e2e_ms_max / 1000.0)
-        peak, peak_src = peaks()
-        gmm_ms = float(np.mean(score_ms)); bm_ms = float(np.mean(beam_ms))
-        tokens_per_frame = float(counts[:, 1].mean())
-        created_per_frame = float(counts[:, 0].mean())
-        gmm_bytes = M_total * ALG_GMM_BYTES_PER_GAUSS + B * T * (D * 4 + 4 * S)
-        beam_bytes = B * T * tokens_per_frame * ALG_BEAM_BYTES_PER_TOKEN
-        beam_name = "beam_kernel_mp" if int(ds.tree.multipath) else "beam_kernel"
-        score_name = "dnn_gemm_kernel (x%d layers)" % ds.dnn.n_layers if use_dnn else "gmm_score_kernel"
-        if bm_ms >= gmm_ms:
-            dom, dom_ms, dom_bytes = beam_name, bm_ms, beam_bytes
-        else:
-            dom, dom_ms, dom_bytes = score_name, gmm_ms, gmm_bytes
-        ach = dom_bytes / (dom_ms / 1000.0) / 1e9
-        # DRAM traffic of the dominant kernel per launch, scaled from the committed ncu --set full capture
-        traffic, traffic_note = None, "no ncu capture of this kernel build under profiles/"
-        tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tfile):
-            tj = json.load(open(tfile))
-            ent = tj.get(dom)
-            if ent is not None and ent.get("source_sha") != kernel_source_sha():
-                traffic_note = (f"profiles/ncu_traffic.json was captured from another build of {dom} "
-                                f"(source_sha {ent.get('source_sha')} != {kernel_source_sha()}): not reported")
-            elif ent is not None:
-                per = ent.get("bytes_per_utterance_frame", ent.get("bytes_per_frame"))
-                traffic = per * B * T
-                traffic_note = f"ncu dram read+write of this build ({ent.get('capture')}), per utterance-frame x {B * T} utterance-frames"
-        tensor = None
-        if use_dnn:
-            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-            tpeak = float(pk.get("bf16_tflops_sustained", 1400.0))
-            tach = B * T * dnn_flops_per_frame / (gmm_ms / 1000.0) / 1e12
-            tensor = {"bound": "tensor", "kernel": score_name, "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
-                      "note": "algorithmic flops (2*in*out per layer per frame); the kernel issues 3 bf16 MMAs per product term "
-                              "(hi.hi+hi.lo+lo.hi) to meet the 1e-4 tolerance, so 1/3 of peak is the ceiling of this formulation",
-                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback 1.4 PFLOP/s sustained"}
+        value = frames_total / (r["wall_ms"] / 1000.0)
+        e2e = frames_total / (r["e2e_ms"] / 1000.0)
+        roof, scoring = rooflines(r, world)
         line = {
             "metric": "frames/sec (xRT) 20k-word triphone decode", "value": value, "unit": "frames/s", "xRT": value / 100.0,
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall_ms_max / a.steps, "device_event_ms_per_step": dev_ms_max / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"{a.workload}: DNN-HMM {D} -> {ds.dnn.n_layers - 1} x {int(ds.dnn.layer_out[0])} logistic -> {S} states "
-                                    f"(BASELINE configs[3] shape), 20k-word 2-gram, beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
-                                    f"bf16x3 tensor-core arithmetic") if use_dnn else
-                                   (f"{a.workload}: tied-state triphone GMM {S} states x 16 mix x {D} dim, 20k-word 2-gram "
-                                    f"(BASELINE configs[1]), beam {ds.tree.beam_width}, {B} utterances x {T} frames per GPU per step, "
-                                    f"GMM arithmetic mode {a.mode}"),
-                       "utts_per_gpu": B, "frames_per_utt": T,
-                       "l2": "per-step working set (score matrix %.1f GB) exceeds L2; input batch alternates" % (B * T * S * 4 / 1e9),
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["wall_ms"] / a.steps, "device_event_ms_per_step": r["dev_ms"] / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (scoring) + f32 (beam)" if r["use_dnn"] else "f32", "data": "synthetic",
+            "config": {"workload": workload_label(a.workload) + (f"; {B} utterances x {T} frames per GPU per step" +
+                                                                (", bf16x3 tensor-core arithmetic" if r["use_dnn"] else f", GMM arithmetic mode {a.mode}")),
+                       "utts_per_gpu": B, "frames_per_utt": T, "resident_utts_per_gpu": r["resident"], "beam": r["beam_width"],
+                       "l2": "per-step working set (score matrix %.1f GB) exceeds L2; %d distinct utterances per batch, two batches alternate" % (B * T * r["S"] * 4 / 1e9, B),
                        "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_note": traffic_note,
-                         "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
-                         "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
-                         "gmm_fp32_tflops": B * T * M_total * ALG_FLOPS_PER_GAUSS_FRAME / (gmm_ms / 1000.0) / 1e12,
-                         "gmm_hbm_gbs": gmm_bytes / (gmm_ms / 1000.0) / 1e9,
-                         "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "heap_extract", "heap_build"), phase)},
-                         "beam_tokens_per_frame": tokens_per_frame, "beam_created_per_frame": created_per_frame},
-            "roofline_scoring": tensor,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
-                    "ms_per_step": e2e_ms_max / a.steps},
-            "gpu_launches": int(launches),
-            "decoded_ok": f"{n_ok}/{len(res)}", "heap_misspeculations": dec.misspeculations(),
-            "heap_levels_per_extraction": round(hs["levels"] / max(hs["extractions"], 1), 3), "clocks": clocks,
+            "roofline": roof, "roofline_scoring": scoring,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"] // a.steps, "d2h_bytes_per_step": r["d2h"] // a.steps,
+                    "ms_per_step": r["e2e_ms"] / a.steps},
+            "gpu_launches": r["launches"],
+            "decoded_ok": f"{r['n_ok']}/{r['n_res']}", "heap_misspeculations": r["misspec"], "clocks": r["clocks"],
         }
+        line.update(extra)
         if world == 1 and not a.no_cpu_baseline:
             try:
                 upp = a.cpu_sample_utts or 1
-                r = reference_measure(a.workload, upp, T, 4242)
-                line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["nproc"], "kind": "reference",
-                                        "sample": f"{r['nproc']} reference processes (one per usable physical core) x {upp} utterances x {T} frames of the "
+                rr = reference_measure(a.workload, upp, T, 4242)
+                line["cpu_baseline"] = {"value": rr["value"], "unit": "frames/s", "cores": rr["nproc"], "kind": "reference",
+                                        "sample": f"{rr['nproc']} reference processes (one per usable core) x {upp} utterances x {T} frames of the "
                                                   f"same workload after a 100-frame warm-up utterance; decode time between PASS1_BEGIN/END, slowest process",
-                                        **{k: r[k] for k in ("nproc", "cpu_count", "affinity", "cgroup_quota", "frames_per_s_per_process",
-                                                             "probe_frames_per_s_1proc", "oversubscribed")}}
+                                        **{k: rr[k] for k in ("nproc", "cpu_count", "affinity", "cgroup_quota", "frames_per_s_per_process",
+                                                              "probe_frames_per_s_1proc", "oversubscribed")}}
             except Exception as e:   # the bench line must still print
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))

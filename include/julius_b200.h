@@ -149,8 +149,12 @@ int jb200_decoder_sync_timing(jb200_decoder *d);
 int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d);
 /* how often (frames, since create) the beam cut had to fall back to the plain sequential replay (0 unless forced) */
 int64_t jb200_decoder_misspeculations(jb200_decoder *d);
-/* beam-cut replay counters since create: out[0] fall-backs, out[1] heap levels walked, out[2] extractions */
+/* beam-cut replay counters since create: out[0] fall-backs to the plain sequential loop, out[1] replay ticks (tree
+ * levels with the single-thread replay), out[2] extractions replayed */
 int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]);
+/* beam cuts that select the top of the token set (sort_token_upward) since create: out[0] how many,
+ * out[1] how many of them were answered by the closed form (score, pre-order position) instead of a replay */
+int jb200_decoder_select_stats(jb200_decoder *d, int64_t out[2]);
 /* how many utterances (thread blocks) are co-resident on the device for this decoder */
 int jb200_decoder_resident_utts(const jb200_decoder *d);
 /* SM-cycle totals per kernel phase of the first n_utts utterances of the last batch: cycles [n_utts][8]

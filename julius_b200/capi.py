@@ -70,6 +70,7 @@ def lib():
             L.jb200_decoder_misspeculations.argtypes = [vp]
             L.jb200_decoder_misspeculations.restype = C.c_int64
             L.jb200_decoder_heap_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+            L.jb200_decoder_select_stats.argtypes = [vp, C.POINTER(C.c_int64)]
             L.jb200_decoder_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
         _lib = L
     return _lib
@@ -253,7 +254,10 @@ class Decoder:
         """beam-cut replay counters since create"""
         v = (C.c_int64 * 3)()
         _check(lib().jb200_decoder_heap_stats(self._h, v), "jb200_decoder_heap_stats")
-        return {"fallbacks": int(v[0]), "levels": int(v[1]), "extractions": int(v[2])}
+        w = (C.c_int64 * 2)()
+        _check(lib().jb200_decoder_select_stats(self._h, w), "jb200_decoder_select_stats")
+        return {"fallbacks": int(v[0]), "levels": int(v[1]), "extractions": int(v[2]),
+                "upward_selects": int(w[0]), "closed_form": int(w[1])}
 
     def resident_utts(self) -> int:
         return int(lib().jb200_decoder_resident_utts(self._h))

@@ -104,9 +104,12 @@ struct BeamParams {
   jb200_utt_result *results; int *words;
   long long *prof;            // [n_utts][8] cycle counters per phase, or NULL
   unsigned *bitmask; int *wordpre;   // per-utterance arrival-order bitmask [maxbits/32] and its word prefix counts
-  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine, heap_single;
+  unsigned long long *misspec_counter; int force_seq_heap, check_heap, no_lose, prof_fine, heap_single, no_closed;
   unsigned long long *lmc; int lmc_bits;      // memo of max_successor_prob, 2^lmc_bits entries (0 = off)
   int maxt, maxc, maxw, maxbits;
+  // token sets too large for shared memory (wide beams on large trees): the heap-select array lives in global memory
+  // ([n_utts][maxt+4] entries) and shared memory only holds the closed form's sort area (sort_cap 8-byte keys)
+  unsigned long long *heap_g; int sort_cap;
   // grammar (DFA) mode, appended so that the offsets of everything above stay what the N-gram kernels were built with
   const uint8_t *cp_allowed; const int *init_node; const float *init_lscore; int n_init; float penalty1;
 };
@@ -354,6 +357,71 @@ __device__ void heap_extract_seq(unsigned long long *A, int n, int extract) {
   __syncthreads();
 }
 
+// The pipelined replay (heap_pipe.cuh) for a heap in GLOBAL memory -- the token set of a wide beam on a large tree does
+// not fit shared memory (-b 4000 on the 60k-word tree: up to 34k tokens a frame).  Same schedule, plain generic loads and
+// stores that bypass L1 (another lane wrote the line one tick ago); a tick costs an L2 round trip instead of a
+// shared-memory one, so this path is for the frames the closed form cannot answer.  outs: shared memory.
+__device__ __forceinline__ ulonglong2 ldcg_pair(const unsigned long long *p) {
+  const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+  return make_ulonglong2(((unsigned long long)v.y << 32) | v.x, ((unsigned long long)v.w << 32) | v.z);
+}
+template <bool MAXHEAP>
+__device__ void heap_extract_pipe_global(unsigned long long *A, const int n, const int extract, const float lose_below,
+                                         unsigned long long *outs, const int maxt, unsigned &ticks_out, unsigned &stalls_out) {
+  constexpr int NL = 16;
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long sent = MAXHEAP ? 0xff800000ull : 0x7f800000ull;
+  const int cap = (maxt >> 1) + 1;                          // pair (maxt+2, maxt+3): always sentinels
+  bool act = false;
+  int slot = 0, cur = cap, my_x = 0;                        // hole index, pair index of its children (slots 2cur, 2cur+1)
+  unsigned long long s = sent;
+  int next_x = 0, wait = 0;
+  unsigned ticks = 0, stalls = 0;
+  if (lane == 0 && extract > 0) outs[0] = __ldcg(A + 1);
+  while (true) {
+    // (1) children pair of the hole
+    ulonglong2 pr = make_ulonglong2(sent, sent);
+    if (act) pr = ldcg_pair(A + 2 * cur);
+    // (2) fill the hole, move one level down or end
+    if (act) {
+      const float xv = hval(pr.x), yv = hval(pr.y), sv = hval(s);
+      const bool right = hcmp<MAXHEAP>(xv, yv);
+      const unsigned long long c = right ? pr.y : pr.x;
+      const float cv = hval(c);
+      const bool stop = hstop<MAXHEAP>(sv, cv) || (MAXHEAP && cv < lose_below);
+      const unsigned long long put = stop ? s : c;
+      __stcg(A + slot, put);
+      if (slot == 1) outs[my_x + 1] = put;
+      if (stop) act = false;
+      else { slot = 2 * cur + (right ? 1 : 0); cur = min(slot, cap); }
+    }
+    __syncwarp();
+    // (3) may the next extraction start?  (holes as they are after the move)
+    if (--wait <= 0) {
+      if (next_x >= extract) { if (!__any_sync(FULL, act)) break; }
+      else {
+        const int ms = n - next_x;
+        const int ln = next_x & (NL - 1);
+        bool blocks = act && ((int)lane == ln);
+        const int dh = 31 - __clz(max(slot, 1)), dms = 31 - __clz(ms);
+        blocks = blocks || (act && dms >= dh && (ms >> (dms - dh)) == slot);
+        if (!__any_sync(FULL, blocks)) {
+          if ((int)lane == ln) {
+            s = __ldcg(A + ms);
+            __stcg(A + ms, sent);
+            my_x = next_x; act = true; slot = 1; cur = 1;
+          }
+          next_x++; wait = 2;
+        } else stalls++;
+      }
+    }
+    __syncwarp();
+    ticks++;
+  }
+  ticks_out = ticks; stalls_out = stalls;
+}
+
 __device__ __forceinline__ void lds_pair(unsigned addr, unsigned &x0, unsigned &x1, unsigned &y0, unsigned &y1) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(addr) : "memory");
 }
@@ -431,10 +499,12 @@ __device__ void heap_extract_fast(unsigned long long *A, const int n, const int 
                                   unsigned long long *outv, const int maxt, unsigned long long *stats,
                                   const SlotClear *idle_work = nullptr, const int single_thread = 0) {
   if (threadIdx.x >= 32 && idle_work) idle_work->run((int)threadIdx.x - 32, BEAM_THREADS - 32);
-  if (single_thread != 1) {
+  if (single_thread != 1 || !__isShared(A)) {
     // warp 0: up to 16 extractions in flight, one tree level per tick each (heap_pipe.cuh)
     if (threadIdx.x < 32) {
       unsigned ticks, stalls;
+      if (!__isShared(A)) heap_extract_pipe_global<MAXHEAP>(A, n, extract, lose_below, outv, maxt, ticks, stalls);
+      else
       if (single_thread == 2) heap_extract_pipe_warp<MAXHEAP>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
       else heap_extract_pipe_warp4<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
       if (threadIdx.x == 0) {
@@ -474,6 +544,107 @@ __device__ void heap_extract_fast(unsigned long long *A, const int n, const int 
   __syncthreads();
 }
 #undef JB_HEAP_LEVEL
+
+// ---- closed form of an upward select ------------------------------------------------------------------------------
+// When every sift of the extraction loop ends on a loser (an element that is never extracted) an extraction is a pure
+// "pull-up": the hole at the root is filled by the larger child (the left one on a tie), and so on down.  Two elements of
+// equal score then keep their relative PRE-ORDER position in the tree for ever -- the one in the right subtree of their
+// lowest common ancestor could only overtake by being strictly larger than everything in the left subtree -- and the
+// root is first in pre-order, hence
+//        extraction order = (score descending, pre-order position in the BUILT heap ascending).
+// A re-inserted winner (the tail slot an extraction takes holds an element that will itself be extracted) sinks from the
+// root instead and may land ahead of elements it ties with; it cannot disturb the order of anybody else.  Such an
+// element e sits in a tail slot p of the built heap (tail slots are leaves, nothing is promoted into a leaf, so a tail
+// slot holds its original content or an earlier extraction's s, itself a tail content) and when p is taken, at step
+// k = n-p+1, the k-1 elements extracted so far and the d = depth(p) elements on the slots above p are all ahead of e.
+// So if  rank(e) < k + d  for every tail element that ties with another candidate, no re-insertion can matter and the
+// closed form is exact; otherwise the caller replays the loop (heap_extract_fast).  On the 20k-word workload the test
+// passes in 56 % of the frames (tools/heapstat.cpp); tools/heapsim.cpp checks form + test against the plain loop.
+//
+// All threads call it after heap_build<true>.  Candidates = elements >= lose_below (a lower bound of the need-th largest
+// score); they are sorted with a bitonic network in `keys` (shared memory: the free part of the heap array, slots
+// n+1.., or a dedicated area when the heap itself lives in global memory), keys
+//   [ order-preserving score key : 32 | 0xffff - pre-order position : 16 | candidate index : 16 ]  descending,
+// payload (slot << 16 | token id) in `pay`.  Returns 1 and fills ordn[0..need) (visiting order = reverse extraction order)
+// or returns 0 with the heap intact (everything above slot n must be padded again before a replay).
+__device__ __forceinline__ int closed_subtree_size(const int c, const int n, const int H) {
+  const int dc = 31 - __clz(c);
+  if (dc > H) return 0;
+  const int sh = H - dc;
+  const int first = c << sh, width = 1 << sh;
+  return (width - 1) + max(0, min(n - first + 1, width));
+}
+__device__ int heap_select_closed(unsigned long long *heap, const int n, const int need, const float lose_below, const int maxt,
+                                  unsigned long long *keys, const int key_cap, unsigned *pay, const int pay_cap,
+                                  int *ordn, int *s_scratch /* [2] shared ints */) {
+  const int tid = threadIdx.x;
+  if (n >= 65536 || maxt >= 65536 || !(lose_below > -INFINITY)) return 0;
+  if (tid == 0) { s_scratch[0] = 0; s_scratch[1] = 0; }
+  __syncthreads();
+  // 1. candidates (a handle per candidate from a shared counter, one atomic per warp and pass)
+  const int H = 31 - __clz(n);
+  const int cap = min(min(key_cap, pay_cap), 65535);
+  for (int h0 = 1; h0 <= n; h0 += BEAM_THREADS) {
+    const int h = h0 + tid;
+    unsigned long long e = 0ull;
+    bool is_c = false;
+    if (h <= n) { e = heap[h]; is_c = (hval(e) >= lose_below); }
+    const unsigned m = __ballot_sync(0xffffffffu, is_c);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&s_scratch[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is_c) {
+      const int ci = base + __popc(m & ((1u << (tid & 31)) - 1u));
+      if (ci < cap) {
+        // pre-order position of slot h in the complete tree of n slots
+        int pre = 0, cur = 1;
+        for (int b = (31 - __clz(h)) - 1; b >= 0; b--) {
+          const int bit = (h >> b) & 1;
+          pre += 1 + (bit ? closed_subtree_size(cur * 2, n, H) : 0);
+          cur = cur * 2 + bit;
+        }
+        keys[ci] = ((unsigned long long)fkey(hval(e)) << 32) | ((unsigned long long)(0xffffu - (unsigned)pre) << 16) | (unsigned)ci;
+        pay[ci] = ((unsigned)h << 16) | (unsigned)(e >> 32);
+      }
+    }
+  }
+  __syncthreads();
+  const int nc = s_scratch[0];
+  int np = 1; while (np < nc) np <<= 1;
+  if (nc > cap || np > key_cap || nc < need) return 0;      // uniform: s_scratch[0] is read after the barrier
+  for (int i = nc + tid; i < np; i += BEAM_THREADS) keys[i] = 0ull;
+  __syncthreads();
+  // 2. bitonic sort, descending
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < (np >> 1); i += BEAM_THREADS) {
+        const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a | j;
+        const unsigned long long ka = keys[a], kb = keys[b];
+        const bool desc = ((a & k) == 0);
+        if (desc ? (ka < kb) : (ka > kb)) { keys[a] = kb; keys[b] = ka; }
+      }
+      __syncthreads();
+    }
+  }
+  // 3. the test: no tail element that ties with another candidate can still be in its slot when the slot is taken
+  const unsigned theta = (unsigned)(keys[need - 1] >> 32);
+  for (int i = tid; i < nc; i += BEAM_THREADS) {
+    const unsigned long long ki = keys[i];
+    const unsigned sk = (unsigned)(ki >> 32);
+    if (sk < theta) continue;
+    const bool tied = (i > 0 && (unsigned)(keys[i - 1] >> 32) == sk) || (i + 1 < nc && (unsigned)(keys[i + 1] >> 32) == sk);
+    if (!tied) continue;
+    const int slot = (int)(pay[(unsigned)ki & 0xffffu] >> 16);
+    if (slot < n - need + 1) continue;
+    const int kstep = n - slot + 1, d = 31 - __clz(slot);
+    if (i + 1 >= kstep + d) s_scratch[1] = 1;
+  }
+  __syncthreads();
+  if (s_scratch[1]) return 0;
+  // 4. survivors in visiting order: last extracted first
+  for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(pay[(unsigned)keys[need - 1 - k] & 0xffffu] & 0xffffu);
+  return 1;
+}
 
 // phase cycle accounting (thread 0 only; negligible cost)
 #define PROF_MARK(k) do { if (tid == 0) { long long _n = clock64(); s_prof[k] += _n - s_tprev; s_tprev = _n; } } while (0)
@@ -675,11 +846,13 @@ beam_kernel_mp(const BeamParams p) {
   const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
   const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
 
-  unsigned long long *heap = reinterpret_cast<unsigned long long *>(beam_smem);
-  int *offs = reinterpret_cast<int *>(heap + MAXT + 4);
+  // shared memory: [heap (MAXT+4 entries) | offs], or, when the heap lives in global memory, [sort area | offs]
+  unsigned long long *const smem_q = reinterpret_cast<unsigned long long *>(beam_smem);
+  unsigned long long *heap = p.heap_g ? p.heap_g + (size_t)blockIdx.x * (MAXT + 4) : smem_q;
+  int *offs = reinterpret_cast<int *>(smem_q + (p.heap_g ? p.sort_cap : MAXT + 4));
   int *hist = offs;                                                               // reused by select #2
   __shared__ int s_warp[NWARP + 1];
-  __shared__ int s_E, s_natoms, s_ns, s_cur, s_overflow, s_found;
+  __shared__ int s_E, s_natoms, s_ns, s_cur, s_overflow, s_found, s_cf[2];
   __shared__ unsigned s_pmaxkey, s_hmaxkey, s_losekey;
   __shared__ unsigned long long s_webest;
   __shared__ float s_thr;
@@ -1133,12 +1306,22 @@ beam_kernel_mp(const BeamParams p) {
         __syncthreads();
         const unsigned lk = s_losekey;
         const float lose_below = (lk == 0u || p.no_lose) ? -INFINITY : __uint_as_float((lk & 0x80000000u) ? (lk & 0x7fffffffu) : ~lk);
-        heap_pad_sentinels<true>(heap, ncre, MAXT);
         heap_build<true>(heap, ncre); PROF_MARK(7);
         const SlotClear sc{tn, ncre, slots};
         slots_clean = true;
-        heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, &sc, p.heap_single);
-        for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
+        int closed = 0;
+        if (!p.no_closed) {
+          sc.run((int)threadIdx.x, BEAM_THREADS);
+          closed = heap_select_closed(heap, ncre, need, lose_below, MAXT, p.heap_g ? smem_q : heap + ncre + 1, p.heap_g ? p.sort_cap : MAXT + 3 - ncre,
+                                      reinterpret_cast<unsigned *>(offs), 2 * (p.beam + 2), ordn, s_cf);
+          if (tid == 0) { atomicAdd(p.misspec_counter + 4, 1ull); if (closed) atomicAdd(p.misspec_counter + 5, 1ull); }
+        }
+        if (!closed) {
+          heap_pad_sentinels<true>(heap, ncre, MAXT);
+          __syncthreads();
+          heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, p.no_closed ? &sc : nullptr, p.heap_single);
+          for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
+        }
       } else {
         ns_new = need;
         heap_pad_sentinels<false>(heap, ncre, MAXT);
@@ -1402,6 +1585,23 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   // in shared memory, and what it takes is lost to L1 (5*beam+startnum at -b 800 costs 30 % of the kernel's speed).
   int maxt = (std::max(4 * t->beam_width + t->n_start, 5 * t->beam_width) + 64 + 3) & ~3;
   if (const char *e = getenv("JB200_MAXT")) maxt = (std::max(atoi(e), 64) + 3) & ~3;
+  // Where the heap-select array lives.  Shared memory as long as one block's share fits; a wide beam on a large tree
+  // (-b 4000 on the 60k-word multipath tree creates up to 8.5 x beam tokens a frame) goes to global memory instead,
+  // with room for 9 x beam + startnum tokens, and shared memory keeps only the closed form's sort area.
+  const size_t offs_bytes = (size_t)(t->beam_width + 2) * 4 * 2;
+  int smem_limit = 0;
+  TRYC(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+  smem_limit -= 2048;                                       // static shared variables of the kernels
+  bool heap_global = (size_t)(maxt + 4) * 8 + offs_bytes > (size_t)smem_limit / 2;   // would leave one block per SM
+  if (const char *e = getenv("JB200_HEAP_GLOBAL")) heap_global = atoi(e) != 0;
+  P.heap_g = nullptr; P.sort_cap = 0;
+  if (heap_global) {
+    if (!getenv("JB200_MAXT")) maxt = std::min(65000, (std::max(maxt, 9 * t->beam_width + t->n_start) + 3) & ~3);
+    int sc = 1024; while (sc < 2 * t->beam_width && sc < 16384) sc <<= 1;       // candidates = beam + one histogram bin
+    if ((size_t)sc * 8 + offs_bytes > (size_t)smem_limit) { set_error("beam width %d needs more shared memory than the device has", t->beam_width); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
+    P.sort_cap = sc;
+    TRY(dev_alloc(d, (size_t)max_utts * (maxt + 4), &P.heap_g));
+  }
   P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.tok));
   TRY(dev_alloc(d, (size_t)max_utts * 2 * maxt, &P.order));
@@ -1415,8 +1615,8 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.maxbits = (P.maxc + std::min(P.maxw, 256) * n_isoent + std::max(t->n_shared, P.n_sharc) + 63) & ~31;
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.bitmask));
   TRY(dev_alloc(d, (size_t)max_utts * (P.maxbits >> 5), &P.wordpre));
-  TRY(dev_alloc(d, 4, &P.misspec_counter));        // [0] mis-speculations, [1] sift levels, [2] extractions
-  TRYC(cudaMemset(P.misspec_counter, 0, 4 * sizeof(unsigned long long)));
+  TRY(dev_alloc(d, 8, &P.misspec_counter));        // [0] mis-speculations, [1] replay ticks (levels), [2] extractions, [3] held-back starts, [4] upward selects, [5] of which closed form
+  TRYC(cudaMemset(P.misspec_counter, 0, 8 * sizeof(unsigned long long)));
   P.force_seq_heap = getenv("JB200_FORCE_SEQ_HEAP") ? atoi(getenv("JB200_FORCE_SEQ_HEAP")) : 0;
   P.check_heap = getenv("JB200_CHECK_HEAP") ? atoi(getenv("JB200_CHECK_HEAP")) : 0;
   {
@@ -1432,6 +1632,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   }
   P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
+  P.no_closed = getenv("JB200_NO_CLOSED_FORM") ? atoi(getenv("JB200_NO_CLOSED_FORM")) : 0;   // 1: always replay the extraction loop
   P.heap_single = getenv("JB200_HEAP_SINGLE") ? atoi(getenv("JB200_HEAP_SINGLE")) : 0;   // 1: the single-thread replay, 2: the branchy pipelined loop (A/B timing)
   {
     size_t tot = (size_t)max_utts * n;
@@ -1457,7 +1658,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_atoms, sizeof(jb200_atom) * (size_t)d->atoms_cap));
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
-  d->smem_bytes = (size_t)(maxt + 4) * 8 + (size_t)(t->beam_width + 2) * 4 * 2;
+  d->smem_bytes = (heap_global ? (size_t)P.sort_cap * 8 : (size_t)(maxt + 4) * 8) + offs_bytes;
   d->grammar = grammar;
   const void *kern = grammar ? (const void *)beam_kernel_grammar : P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
   TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
@@ -1584,6 +1785,15 @@ extern "C" int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]) {
   JB_CUDA(cudaSetDevice(d->device));
   JB_CUDA(cudaMemcpy(v, d->P.misspec_counter, sizeof(v), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 3; i++) out[i] = (int64_t)v[i];
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_select_stats(jb200_decoder *d, int64_t out[2]) {
+  if (!d || !out) { set_error("bad argument"); return JB200_ERR_ARG; }
+  unsigned long long v[2] = {0, 0};
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaMemcpy(v, d->P.misspec_counter + 4, sizeof(v), cudaMemcpyDeviceToHost));
+  out[0] = (int64_t)v[0]; out[1] = (int64_t)v[1];
   return JB200_OK;
 }
 

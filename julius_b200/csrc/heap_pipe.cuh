@@ -232,4 +232,91 @@ __device__ __forceinline__ void heap_extract_pipe_warp4(unsigned long long *A, c
   ticks_out = ticks; stalls_out = stalls;
 }
 
+// ---- a leaner bookkeeping of the same schedule (candidate for the shipped loop; FLAGS as above).  Every lane knows the
+// extractions it owns (my_x = lane, lane+16, ...), where their tail slot and their output entry live, and has the tail
+// slot's content prefetched one round (32 ticks) ahead -- a loser stays a loser, and a non-loser only sends the start
+// through the ancestor vote, where s is read afresh anyway.  A start then costs one compare, one ballot and a handful of
+// predicated updates instead of recomputing all of it from next_x.
+template <bool MAXHEAP, int FLAGS>
+__device__ __forceinline__ void heap_extract_pipe_warp5(unsigned long long *A, const int n, const int extract, const float lose_below,
+                                                        unsigned long long *outs, const int maxt, const unsigned lane,
+                                                        unsigned &ticks_out, unsigned &stalls_out) {
+  constexpr int NL = 16;
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned hb = hp_smem_u32(A);
+  const unsigned ob = hp_smem_u32(outs);
+  const unsigned sent = MAXHEAP ? 0xff800000u : 0x7f800000u;
+  const unsigned capa = hb + (((unsigned)(maxt >> 1) + 1u) << 4);
+  const unsigned root = hb + 8u;
+  float lose_dn = lose_below;
+  if (MAXHEAP && lose_below > -INFINITY) {
+    unsigned b = __float_as_uint(lose_below);
+    b = (lose_below > 0.0f) ? b - 1u : (lose_below < 0.0f) ? b + 1u : 0x80000001u;
+    lose_dn = __uint_as_float(b);
+  }
+  bool act = false;
+  unsigned slot = capa, cur = capa;
+  unsigned s_lo = sent, s_hi = 0u;
+  int my_x = (lane < NL) ? (int)lane : 0x7fffffff;         // the next extraction this lane owns
+  unsigned my_ma = hb + ((unsigned)(n - (int)lane) << 3);   // its tail slot
+  unsigned my_out = ob + ((lane + 1u) << 3);                // where its root write goes: outs[my_x + 1]
+  unsigned out_w = ob;                                      // the same for the extraction in flight
+  unsigned nxt_lo = sent, nxt_hi = 0u;
+  hp_lds_one_if(my_x < extract, my_ma, nxt_lo, nxt_hi);
+  int next_x = 0, wait = 0;
+  unsigned ticks = 0, stalls = 0;
+  if (lane == 0 && extract > 0) outs[0] = A[1];
+  while (true) {
+    unsigned x0, x1, y0, y1;
+    hp_lds_pair(cur, x0, x1, y0, y1);
+    {
+      const unsigned base2 = (cur << 1) - hb;
+      const float sv = __uint_as_float(s_lo), xv = __uint_as_float(x0), yv = __uint_as_float(y0);
+      const float thr = MAXHEAP ? fmaxf(sv, lose_dn) : sv;
+      const bool right = MAXHEAP ? (xv < yv) : (xv > yv);
+      const float cv = MAXHEAP ? fmaxf(xv, yv) : fminf(xv, yv);
+      const bool stop = MAXHEAP ? (cv <= thr) : (cv >= thr);
+      const unsigned c_lo = right ? y0 : x0, c_hi = right ? y1 : x1;
+      const unsigned p_lo = stop ? s_lo : c_lo, p_hi = stop ? s_hi : c_hi;
+      hp_sts_one_if(act, slot, p_lo, p_hi);
+      hp_sts_one_if(act && slot == root, out_w, p_lo, p_hi);
+      slot = cur + (right ? 8u : 0u);
+      cur = min(base2 + (right ? 16u : 0u), capa);
+      act = act && !stop;
+    }
+    if (--wait <= 0) {
+      if (next_x >= extract) {
+        if (!__any_sync(FULL, act)) break;
+      } else {
+        const bool mine = (my_x == next_x);
+        const bool careful = mine && !(MAXHEAP && (__uint_as_float(nxt_lo) < lose_below));
+        bool ok = true;
+        if (__any_sync(FULL, careful)) {                                     // rare with the loser cut
+          const unsigned ms = (unsigned)(n - next_x);
+          const unsigned h = (slot - hb) >> 3;
+          const int dh = 31 - __clz(h), dms = 31 - __clz(ms);
+          ok = !__any_sync(FULL, act && dms >= dh && (ms >> (dms - dh)) == h);
+        }
+        if (ok) {
+          hp_lds_one_if(mine, my_ma, s_lo, s_hi);                            // s = A[m]
+          hp_sts_one_if(mine, my_ma, sent, 0u);                              // slot m leaves the heap
+          out_w = mine ? my_out : out_w;
+          slot = mine ? root : slot;
+          cur = mine ? hb + 16u : cur;
+          act = act || mine;
+          my_x += mine ? NL : 0;
+          my_ma -= mine ? (unsigned)(NL * 8) : 0u;
+          my_out += mine ? (unsigned)(NL * 8) : 0u;
+          hp_lds_one_if(mine && my_x < extract, my_ma, nxt_lo, nxt_hi);      // next round's tail content
+          next_x++;
+          wait = 2;
+        } else stalls++;
+      }
+    }
+    if (!(FLAGS & 1)) __syncwarp();
+    ticks++;
+  }
+  ticks_out = ticks; stalls_out = stalls;
+}
+
 }  // namespace jb200

@@ -73,6 +73,9 @@ class SynthConfig:
             return SynthConfig(name="tri20k", seed=4, n_phones=36, n_states=3000, n_mix=16,
                                phys_per_phone=84, vocab=20000, n_bigrams=200000,
                                min_wlen=3, max_wlen=8, one_phone_words=0)
+        if name == "tri60k":     # BASELINE config[4]: the same AM, 60k words, short-pause model for -iwsp
+            c = SynthConfig.preset("tri20k")
+            return dataclasses.replace(c, name="tri60k", vocab=60000, n_bigrams=600000, sp_model=True)
         raise KeyError(name)
 
 
@@ -307,13 +310,10 @@ class SynthModel:
         return paths
 
     # ------------------------------------------------------------------ features
-    def sample_utterance(self, rng: np.random.Generator, n_frames: int, noise: float = 1.0, word_seq=None):
-        """Sample ~n_frames feature frames along a random ``<s> w.. </s>`` path.
-
-        Returns (feats [T, D] float32, word index list).  T is exactly n_frames:
-        words are appended until the budget is reached and the tail is padded
-        with trailing silence so every utterance ends inside ``</s>``.
-        """
+    def sample_state_path(self, rng: np.random.Generator, n_frames: int, word_seq=None):
+        """A random ``<s> w.. </s>`` path through the tied states: (state ids [n_frames] int64, word index list).
+        Words are appended until the frame budget is reached and the tail is padded with trailing silence so
+        every utterance ends inside ``</s>``."""
         cfg = self.cfg
         states = []
         words = []
@@ -352,7 +352,13 @@ class SynthModel:
             states = states[: n_frames - len(tail)] + tail
         while len(states) < n_frames:
             states.append(sil_states[2])
-        st = np.asarray(states[:n_frames], dtype=np.int64)
+        return np.asarray(states[:n_frames], dtype=np.int64), words
+
+    def sample_utterance(self, rng: np.random.Generator, n_frames: int, noise: float = 1.0, word_seq=None):
+        """Sample n_frames feature frames along a random ``<s> w.. </s>`` path (sample_state_path), each frame drawn
+        from one Gaussian of its state.  Returns (feats [T, D] float32, word index list)."""
+        cfg = self.cfg
+        st, words = self.sample_state_path(rng, n_frames, word_seq)
         comp = np.array([rng.choice(cfg.n_mix, p=self.weight[s].astype(np.float64) / float(self.weight[s].astype(np.float64).sum())) for s in st])
         mu = self.mean[st, comp]
         sd = np.sqrt(self.var[st, comp])
@@ -390,39 +396,107 @@ class DnnConfig:
     hidden: int = 64
     layers: int = 2
     seed: int = 5
+    # Benchmark workloads ("prototype" output layer): a random-init logistic stack of this depth with the default
+    # weight scale maps every input to (almost) the same hidden vector, so the posteriors do not depend on the frame
+    # at all and the beam search degenerates.  With w_scale ~ 8 the hidden layers keep the inputs apart, and the output
+    # layer is set, instead of drawn, to the nearest-prototype classifier  logit_s(h) = proto_gain * (h_s - hbar).(h - hbar)
+    # over one prototype input per state -- the stand-in for a trained network: on the prototype of state s the
+    # network is confident of s.  Utterances then emit the prototypes along an HMM state path.
+    w_scale: float = 1.5
+    prototype_output: bool = False
+    proto_gain: float = 0.03
+    cache_dir: str = ""        # where the (BLAS-order dependent) prototype output layer is kept so every reader sees the same bits
+
+
+_DNN_CACHE = {}
+
+
+def dnn_arrays(n_states: int, cfg: DnnConfig) -> dict:
+    """The synthetic DNN of a config: W{i} (out,in) and B{i} (out,1) as '<f4', output layer Wo/Bo, Dirichlet state
+    priors (and, for prototype_output, the per-state prototype inputs "proto").  One seeded draw order, shared by
+    write_dnn (files for the reference) and dnn_blob_entries (flattened)."""
+    key = (n_states, dataclasses.astuple(cfg))
+    if key in _DNN_CACHE:
+        return _DNN_CACHE[key]
+    rng = np.random.default_rng(cfg.seed)
+    dims = [cfg.in_dim] + [cfg.hidden] * cfg.layers
+    arrays = {}
+    for i in range(cfg.layers):
+        arrays[f"W{i + 1}"] = (rng.standard_normal((dims[i + 1], dims[i])) * (cfg.w_scale / np.sqrt(dims[i]))).astype("<f4")
+        arrays[f"B{i + 1}"] = (rng.standard_normal((dims[i + 1], 1)) * 0.1).astype("<f4")
+        if cfg.prototype_output and i > 0:
+            # logistic activations average 0.5: centre each unit's input on that (bias = -0.5 * sum of its weights),
+            # or the common component saturates every unit the same way for all inputs and the layers collapse them
+            arrays[f"B{i + 1}"] = (arrays[f"B{i + 1}"] - 0.5 * arrays[f"W{i + 1}"].astype(np.float64).sum(1, keepdims=True)).astype("<f4")
+    arrays["Wo"] = (rng.standard_normal((n_states, cfg.hidden)) * (3.0 / np.sqrt(cfg.hidden))).astype("<f4")
+    arrays["Bo"] = (rng.standard_normal((n_states, 1)) * 0.1).astype("<f4")
+    arrays["prior"] = rng.dirichlet(np.full(n_states, 5.0))
+    if cfg.prototype_output:
+        fn = os.path.join(cfg.cache_dir, f"dnn_proto_s{n_states}_i{cfg.in_dim}_h{cfg.hidden}x{cfg.layers}_seed{cfg.seed}.npz") if cfg.cache_dir else ""
+        if fn and os.path.exists(fn):
+            z = np.load(fn)
+            arrays["proto"], arrays["Wo"], arrays["Bo"] = z["proto"], z["Wo"], z["Bo"]
+        else:
+            proto = rng.standard_normal((n_states, cfg.in_dim)).astype(np.float32)
+            h = proto.astype(np.float64)
+            for i in range(cfg.layers):
+                h = 1.0 / (1.0 + np.exp(-(h @ arrays[f"W{i + 1}"].astype(np.float64).T + arrays[f"B{i + 1}"].astype(np.float64).ravel())))
+            hbar = h.mean(0)
+            hc = h - hbar
+            arrays["proto"] = proto
+            arrays["Wo"] = (cfg.proto_gain * hc).astype("<f4")
+            arrays["Bo"] = (-cfg.proto_gain * (hc @ hbar)).astype("<f4").reshape(-1, 1)
+            if fn:
+                try:
+                    os.makedirs(cfg.cache_dir, exist_ok=True)
+                    np.savez(fn, proto=arrays["proto"], Wo=arrays["Wo"], Bo=arrays["Bo"])
+                except OSError:
+                    pass
+    _DNN_CACHE[key] = arrays
+    return arrays
+
+
+def dnn_blob_entries(n_states: int, cfg: DnnConfig) -> dict:
+    """The same DNN as the flattened-model entries the export plugin produces from the reference's DNNData
+    (julius_b200/plugin/jb200_export.c): layer shapes, row-major (out,in) weights, biases, and the state priors as the
+    reference stores them after loading 'id %.8e' lines with fscanf("%e") and log10-nizing (calc_dnn.c:691-703)."""
+    a = dnn_arrays(n_states, cfg)
+    dims = [cfg.in_dim] + [cfg.hidden] * cfg.layers + [n_states]
+    b = {"dnn.n_layers": np.array([cfg.layers + 1], np.int32), "dnn.in_dim": np.array([cfg.in_dim], np.int32),
+         "dnn.out_dim": np.array([n_states], np.int32)}
+    for i in range(cfg.layers + 1):
+        w, bias = (a[f"W{i + 1}"], a[f"B{i + 1}"]) if i < cfg.layers else (a["Wo"], a["Bo"])
+        b[f"dnn.l{i}.in"] = np.array([dims[i]], np.int32)
+        b[f"dnn.l{i}.out"] = np.array([dims[i + 1]], np.int32)
+        b[f"dnn.l{i}.w"] = np.ascontiguousarray(w, np.float32).ravel()
+        b[f"dnn.l{i}.b"] = np.ascontiguousarray(bias, np.float32).ravel()
+    val = np.array([float(f"{p:.8e}") for p in a["prior"]], np.float32) * np.float32(1.0)
+    b["dnn.state_prior"] = np.log10(val.astype(np.float64)).astype(np.float32)
+    return b
 
 
 def write_dnn(outdir: str, n_states: int, cfg: DnnConfig) -> dict:
     """Random-init DNN in the reference's file formats (libsent/src/phmm/calc_dnn.c:225-336,
     libjulius/src/m_jconf.c:579-733): W as C-order (out,in) '<f4' .npy, biases (out,1), prior file
     'state_id prior', and the dnnconf tying them together.  Returns the arrays."""
-    rng = np.random.default_rng(cfg.seed)
     os.makedirs(outdir, exist_ok=True)
-    dims = [cfg.in_dim] + [cfg.hidden] * cfg.layers
-    arrays = {}
+    arrays = dnn_arrays(n_states, cfg)
     lines = ["feature_type USER", "feature_options -notypecheck", f"feature_len {cfg.feature_len}",
              f"context_len {cfg.context_len}", f"input_nodes {cfg.in_dim}", f"output_nodes {n_states}",
              f"hidden_nodes {cfg.hidden}", f"hidden_layers {cfg.layers}"]
     for i in range(cfg.layers):
-        w = (rng.standard_normal((dims[i + 1], dims[i])) * (1.5 / np.sqrt(dims[i]))).astype("<f4")
-        b = (rng.standard_normal((dims[i + 1], 1)) * 0.1).astype("<f4")
-        np.save(os.path.join(outdir, f"W{i + 1}.npy"), w)
-        np.save(os.path.join(outdir, f"B{i + 1}.npy"), b)
-        arrays[f"W{i + 1}"], arrays[f"B{i + 1}"] = w, b
+        np.save(os.path.join(outdir, f"W{i + 1}.npy"), arrays[f"W{i + 1}"])
+        np.save(os.path.join(outdir, f"B{i + 1}.npy"), arrays[f"B{i + 1}"])
         lines += [f"W{i + 1} W{i + 1}.npy", f"B{i + 1} B{i + 1}.npy"]
-    wo = (rng.standard_normal((n_states, cfg.hidden)) * (3.0 / np.sqrt(cfg.hidden))).astype("<f4")
-    bo = (rng.standard_normal((n_states, 1)) * 0.1).astype("<f4")
-    np.save(os.path.join(outdir, "Wo.npy"), wo)
-    np.save(os.path.join(outdir, "Bo.npy"), bo)
-    prior = rng.dirichlet(np.full(n_states, 5.0))
+    np.save(os.path.join(outdir, "Wo.npy"), arrays["Wo"])
+    np.save(os.path.join(outdir, "Bo.npy"), arrays["Bo"])
     with open(os.path.join(outdir, "prior.txt"), "w") as f:
-        for i, p in enumerate(prior):
+        for i, p in enumerate(arrays["prior"]):
             f.write(f"{i} {p:.8e}\n")
     lines += ["output_W Wo.npy", "output_B Bo.npy", "state_prior prior.txt", "state_prior_factor 1.0",
               "state_prior_log10nize yes", "batch_size 1", "num_threads 1"]
     with open(os.path.join(outdir, "dnnconf"), "w") as f:
         f.write("\n".join(lines) + "\n")
-    arrays.update(Wo=wo, Bo=bo, prior=prior)
     return arrays
 
 
@@ -434,3 +508,18 @@ def sample_dnn_input(rng: np.random.Generator, n_frames: int, in_dim: int) -> np
         v = 0.9 * v + 0.45 * rng.standard_normal(in_dim)
         x[t] = v
     return x
+
+
+def sample_dnn_batch(rng: np.random.Generator, n_utts: int, n_frames: int, in_dim: int) -> list:
+    """n_utts independent trajectories of the same process, advanced together (one numpy step per frame for the whole
+    batch instead of one per utterance-frame; float32 noise drawn in blocks of frames)."""
+    x = np.empty((n_utts, n_frames, in_dim), np.float32)
+    v = rng.standard_normal((n_utts, in_dim), dtype=np.float32)
+    blk = 50
+    for t0 in range(0, n_frames, blk):
+        nb = min(blk, n_frames - t0)
+        noise = rng.standard_normal((nb, n_utts, in_dim), dtype=np.float32)
+        for k in range(nb):
+            v = np.float32(0.9) * v + np.float32(0.45) * noise[k]
+            x[:, t0 + k, :] = v
+    return [x[i] for i in range(n_utts)]

@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 
 from julius_b200 import capi
-from util import DNN_CASES, Golden, atoms_equal, rel_err
+from julius_b200 import desc, synth
+from util import DNN_CASES, Golden, atoms_equal, full_dnn_blob, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -51,3 +52,23 @@ def test_decode_with_dnn_scores_matches_reference_words(case):
         assert r["overflow"] == 0 and r["status"] == u.status
         assert r["words"] == u.words
         assert abs(r["score"] - u.score) <= 1e-4 * abs(u.score) + 0.05
+
+
+@pytest.fixture(scope="module")
+def full_dnn():
+    return desc.Descriptors(full_dnn_blob())
+
+
+@pytest.mark.parametrize("T", [1, 127, 129, 300])
+def test_dnn_full_shape_within_1e4_of_the_oracle(full_dnn, T, oracle_lib):
+    """K2 at the BASELINE configs[3] shape, 528 -> 7 x 2048 -> 3000: 24 k-blocks per hidden layer, a partial last
+    column block (3000 = 11 x 256 + 184), TMEM double-buffer wrap-around, ragged frame counts around the 128-row tile.
+    The checker is the CPU restatement of dnn_calc_outprob (calc_dnn.c:774-868), itself pinned bit-exact to the
+    compiled reference on the golden DNN cases."""
+    x = synth.sample_dnn_input(np.random.default_rng(100 + T), T, 528)
+    want = oracle_lib.dnn_score(full_dnn, x)
+    dnn = capi.DnnScorer(full_dnn)
+    got = dnn.score(x)
+    assert got.shape == want.shape == (T, 3000)
+    err = rel_err(got, want, floor=1.0)
+    assert err.max() <= 1e-4, f"max rel err {err.max():.3e}, max abs {np.abs(got - want).max():.3e}"

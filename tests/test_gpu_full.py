@@ -17,7 +17,7 @@ NAME = "tri20k"
 def full():
     if not workload.ready(NAME):
         pytest.skip("workloads/tri20k not prepared (built by __graft_entry__.build())")
-    blob = refdump.load_blob(workload.path(NAME, "model.jb2m"))
+    blob = workload.load_model(NAME)
     ds = desc.Descriptors(blob)
     m = workload.synth_model(NAME)
     am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
@@ -90,7 +90,7 @@ def test_full_size_heap_self_check(monkeypatch, oracle_lib):
     if not workload.ready(NAME):
         pytest.skip("workloads/tri20k not prepared")
     monkeypatch.setenv("JB200_CHECK_HEAP", "1")
-    blob = refdump.load_blob(workload.path(NAME, "model.jb2m"))
+    blob = workload.load_model(NAME)
     ds = desc.Descriptors(blob)
     am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
     dec = capi.Decoder(ds, am, max_utts=8, max_frames=8 * 600)
@@ -111,7 +111,7 @@ def test_other_baseline_configs_end_to_end_vs_oracle(name, frames, oracle_lib):
     safe top-N algorithm for state-tied models), and configs[1] on the multipath tree (-multipath): GPU end to end == CPU restatement, atom for atom."""
     if not workload.ready(name):
         pytest.skip(f"workloads/{name} not prepared")
-    blob = refdump.load_blob(workload.path(name, "model.jb2m"))
+    blob = workload.load_model(name)
     ds = desc.Descriptors(blob)
     m = workload.synth_model(name)
     am = capi.GmmScorer(ds, mode=capi.GMM_EXACT)
@@ -135,7 +135,7 @@ def test_wide_beam_4000_vs_oracle(name, oracle_lib):
     array alone is 140 KB of shared memory, one utterance per SM; ~9000 tokens are created per frame."""
     if not workload.ready(name):
         pytest.skip(f"workloads/{name} not prepared")
-    blob = refdump.load_blob(workload.path(name, "model.jb2m"))
+    blob = workload.load_model(name)
     ds = desc.Descriptors(blob)
     ds.tree.beam_width = 4000
     m = workload.synth_model(name)
@@ -150,3 +150,38 @@ def test_wide_beam_4000_vs_oracle(name, oracle_lib):
         assert ok, why
         assert r["words"] == o["words"] and r["status"] == o["status"]
     assert max(c[1] for c in o["trace"]) > 800      # the wide beam was actually used
+
+
+@pytest.mark.parametrize("name,frames", [("dnn20k", 200), ("dnn60k_mp", 150)])
+def test_dnn_hmm_configs_vs_oracle(name, frames, oracle_lib):
+    """BASELINE.json configs[3] (DNN-HMM 528 -> 7 x 2048 -> 3000 states, 20k words) and configs[4] (the same acoustic
+    model on the 60k-word multipath tree with -iwsp -iwcd1 max -b 4000: one utterance per SM, ~4 x beam tokens a frame).
+    K2's scores are within 1e-4 of the reference, not bit-identical, so the beam is checked twice: bit-exact on the
+    CPU restatement's own score matrix (GPU beam == CPU beam, atom for atom), and end to end (K2 -> K3) by the
+    pass-1 word sequence and score."""
+    if not workload.ready(name):
+        pytest.skip(f"workloads/{name} not prepared")
+    ds = desc.Descriptors(workload.load_model(name))
+    m = workload.synth_model(name)
+    feats = workload.sample_inputs(name, m, 2, frames, seed=61)
+    am = capi.GmmScorer(ds, gmm_desc=ds.cd_only_gmm())
+    dec = capi.Decoder(ds, am, max_utts=2, max_frames=2 * frames)
+    scores = [oracle_lib.dnn_score(ds, x) for x in feats]
+    want = [oracle_lib.beam_decode(ds, sc, trace=True) for sc in scores]
+    for r, o in zip(dec.decode_scores(scores), want):
+        assert r["overflow"] == 0
+        ok, why = atoms_equal(r["atoms"], o["atoms"])
+        assert ok, why
+        assert r["words"] == o["words"] and r["status"] == o["status"]
+    if name == "dnn60k_mp":
+        assert max(c[1] for c in want[0]["trace"]) > 2000      # the wide beam was actually used
+    dnn = capi.DnnScorer(ds)
+    for x, sc in zip(feats, scores):
+        got = dnn.score(x)
+        rel = np.abs(got - sc) / np.maximum(np.maximum(np.abs(got), np.abs(sc)), 1.0)
+        assert rel.max() <= 1e-4
+    dec.attach_dnn(dnn)
+    for r, o in zip(dec.decode(feats), want):
+        assert r["overflow"] == 0 and r["status"] == o["status"]
+        assert r["words"] == o["words"]
+        assert abs(r["score"] - o["score"]) <= 1e-4 * abs(o["score"]) + 0.05

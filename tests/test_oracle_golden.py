@@ -58,3 +58,26 @@ def test_dnn_restatement_bit_exact_and_beam_on_dnn_scores(case, oracle_lib):
         ok, why = atoms_equal(r["atoms"], u.atoms)
         assert ok, why
         assert r["words"] == u.words and r["status"] == u.status
+
+
+def test_dnn_restatement_at_full_shape_agrees_with_fp64(oracle_lib):
+    """The checker of the full-shape K2 test (tests/test_gpu_dnn.py) is the restatement of dnn_calc_outprob run at
+    528 -> 7 x 2048 -> 3000; here it is held against a float64 numpy forward pass with the exact logistic (the
+    reference's table logistic and fp32 FMA accumulation differ from it by a few 1e-5 in log10 units)."""
+    import numpy as np
+    from julius_b200 import desc, synth
+    from util import full_dnn_blob
+    blob = full_dnn_blob()
+    ds = desc.Descriptors(blob)
+    x = synth.sample_dnn_input(np.random.default_rng(1), 6, 528)
+    got = oracle_lib.dnn_score(ds, x)
+    h = x.astype(np.float64)
+    L = int(blob["dnn.n_layers"][0])
+    for i in range(L):
+        w = blob[f"dnn.l{i}.w"].reshape(int(blob[f"dnn.l{i}.out"][0]), int(blob[f"dnn.l{i}.in"][0])).astype(np.float64)
+        h = h @ w.T + blob[f"dnn.l{i}.b"].astype(np.float64)
+        if i < L - 1:
+            h = 1.0 / (1.0 + np.exp(-h))
+    m = h.max(1, keepdims=True)
+    want = (h - (m + np.log(np.exp(h - m).sum(1, keepdims=True)))) / np.log(10.0) - blob["dnn.state_prior"].astype(np.float64)
+    assert np.abs(got - want).max() < 2e-4

@@ -43,3 +43,22 @@ def atoms_equal(a, b):
 def rel_err(a, b, floor=1.0):
     """|a-b| / max(|a|,|b|,floor): the relative criterion with an absolute floor (hard parts)."""
     return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+
+
+def full_dnn_blob(seed=3, in_dim=528, hidden=2048, layers=7, n_out=3000):
+    """A random-init DNN of the BASELINE configs[3] shape (528 = 48 x 11 inputs, 7 x 2048 logistic, n_out states) as a
+    flattened-model blob dict, with the initialisation of julius_b200.synth.write_dnn (W ~ N(0, 1.5/sqrt(in)), output
+    layer 3/sqrt(in), b ~ N(0, 0.1), Dirichlet priors stored as log10, calc_dnn.c:699-703)."""
+    rng = np.random.default_rng(seed)
+    dims = [in_dim] + [hidden] * layers + [n_out]
+    b = {"dnn.n_layers": np.array([layers + 1], np.int32), "dnn.in_dim": np.array([in_dim], np.int32),
+         "dnn.out_dim": np.array([n_out], np.int32), "gmm.n_states": np.array([n_out], np.int32)}
+    for i in range(layers + 1):
+        scale = (3.0 if i == layers else 1.5) / np.sqrt(dims[i])
+        b[f"dnn.l{i}.in"] = np.array([dims[i]], np.int32)
+        b[f"dnn.l{i}.out"] = np.array([dims[i + 1]], np.int32)
+        b[f"dnn.l{i}.w"] = (rng.standard_normal((dims[i + 1], dims[i])) * scale).astype(np.float32).ravel()
+        b[f"dnn.l{i}.b"] = (rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32)
+    prior = rng.dirichlet(np.full(n_out, 5.0))
+    b["dnn.state_prior"] = np.log10(prior).astype(np.float32)
+    return b

@@ -91,7 +91,7 @@ int main(int argc, char **argv) {
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 1;
   long nsel = 0, nup = 0, ndown = 0, sum_n = 0, sum_lv = 0, sum_x = 0;
-  long c1_ok = 0, cf_ok = 0, cf_ok_given_c1 = 0, c1_total = 0;
+  long c1_ok = 0, cf_ok = 0, cf_ok_given_c1 = 0, c1_total = 0, c2_ok = 0, cf_ok_given_c2 = 0;
   long sum_ticks = 0, sum_stalls = 0;
   long sum_tail_win = 0, sum_tie_pairs = 0, sum_reins = 0, sum_reins_tied = 0;
   std::map<int, long> badhist;
@@ -140,6 +140,18 @@ int main(int argc, char **argv) {
     sum_tail_win += tail_w;
     badhist[(int)std::min<long>(bad, 10)]++;
     c1_total++;
+    // condition C2: a tied tail winner e in slot p (taken at step k = n-p+1) can only be re-inserted if its d = depth(p)
+    // ancestors and the k-1 elements extracted before are all ahead of it:  rank(e) >= k + d
+    {
+      std::map<int, int> rank_of;   // id -> 1-based rank in the closed-form order
+      for (size_t i = 0; i < w.size(); i++) rank_of[w[i].id] = (int)i + 1;
+      bool c2 = true;
+      for (int p = n - need + 1; p <= n; p++) if (H0[p].v >= theta && mult[H0[p].v] > 1) {
+        const int k = n - p + 1, d = 31 - __builtin_clz(p);
+        if (rank_of[H0[p].id] >= k + d) c2 = false;
+      }
+      if (c2) { c2_ok++; if (same) cf_ok_given_c2++; }
+    }
     if (c1) { c1_ok++; if (same) cf_ok_given_c1++; }
     if (same) cf_ok++;
   }
@@ -150,6 +162,7 @@ int main(int argc, char **argv) {
          (double)sum_tail_win / nup, (double)sum_reins / nup, (double)sum_tie_pairs / nup);
   printf("C1' holds in %ld of %ld (%.1f%%); closed form correct in %ld (%.1f%%); correct given C1' %ld of %ld\n",
          c1_ok, c1_total, 100.0 * c1_ok / c1_total, cf_ok, 100.0 * cf_ok / c1_total, cf_ok_given_c1, c1_ok);
+  printf("C2 holds in %ld of %ld (%.1f%%); closed form correct given C2 %ld of %ld\n", c2_ok, c1_total, 100.0 * c2_ok / c1_total, cf_ok_given_c2, c2_ok);
   for (auto &kv : badhist) printf("  tail winners tied with another winner = %d : %ld selects\n", kv.first, kv.second);
   return 0;
 }

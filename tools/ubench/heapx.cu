@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
       long long t0 = clock64();
       if (V == 9) jb200::heap_extract_pipe_warp<true>(A, n, extract, lose_below, outg + (size_t)blockIdx.x * 1024, MAXT, threadIdx.x, ticks, stalls);
       else if (V == 14) jb200::heap_extract_pipe_warp4<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
-      else jb200::heap_extract_pipe_warp4<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else if (V == 15) jb200::heap_extract_pipe_warp4<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else if (V == 16) jb200::heap_extract_pipe_warp5<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else jb200::heap_extract_pipe_warp5<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
       long long t1 = clock64();
       if (threadIdx.x == 0) { res[blockIdx.x * 2] = t1 - t0; res[blockIdx.x * 2 + 1] = ticks; }
     }
@@ -300,6 +302,37 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
   if (blockIdx.x == 0 && V == 1) for (int i = threadIdx.x; i < extract_in; i += blockDim.x) outg[i] = outs[i];
 }
 
+// floor of a tick: 16 lanes walk down the heap (read-only) picking the larger child, restarting at the root from a leaf.
+// MODE 0: load + compare + address select only; MODE 1: plus one predicated 8-byte store per level (to a scratch copy of
+// the slot); MODE 2: MODE 1 plus __syncwarp per level.
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) kfloor(const unsigned long long *init, int n, int nticks, long long *res) {
+  __shared__ __align__(16) unsigned long long A[MAXT + 4];
+  __shared__ __align__(16) unsigned long long scratch[64];
+  for (int i = threadIdx.x; i < MAXT + 4; i += blockDim.x) A[i] = (i >= 1 && i <= n) ? init[i] : 0xff800000ull;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned hb = jb200::hp_smem_u32(A), sb = jb200::hp_smem_u32(scratch);
+    const unsigned capa = hb + (((unsigned)(MAXT >> 1) + 1u) << 4);
+    unsigned cur = (threadIdx.x < 16) ? hb + 16u : capa;
+    unsigned acc = 0;
+    long long t0 = clock64();
+    for (int t = 0; t < nticks; t++) {
+      unsigned x0, x1, y0, y1;
+      jb200::hp_lds_pair(cur, x0, x1, y0, y1);
+      const bool right = __uint_as_float(x0) < __uint_as_float(y0);
+      const unsigned base2 = (cur << 1) - hb;
+      unsigned ncur = min(base2 + (right ? 16u : 0u), capa);
+      if (MODE >= 1) jb200::hp_sts_one_if(threadIdx.x < 16, sb + (threadIdx.x << 3), right ? y0 : x0, right ? y1 : x1);
+      acc += right ? y1 : x1;
+      cur = (ncur == capa && threadIdx.x < 16) ? hb + 16u : ncur;
+      if (MODE >= 2) __syncwarp();
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { res[blockIdx.x * 2] = t1 - t0; res[blockIdx.x * 2 + 1] = acc; }
+  }
+}
+
 int main() {
   const int n = 2400, extract = 800;
   std::vector<unsigned long long> h(MAXT + 4, 0);
@@ -331,8 +364,18 @@ int main() {
   cudaMalloc(&d, sizeof(unsigned long long) * (MAXT + 4)); cudaMemcpy(d, h.data(), sizeof(unsigned long long) * (MAXT + 4), cudaMemcpyHostToDevice);
   cudaMalloc(&o, sizeof(unsigned long long) * 1024 * 592); cudaMalloc(&r, sizeof(hr));
   std::vector<unsigned long long> ho(1024);
+  for (int blocks : {1, 592}) for (int mode = 0; mode < 3; mode++) {
+    const int nt = 4000;
+    for (int rep = 0; rep < 2; rep++) {
+      if (mode == 0) kfloor<0><<<blocks, 256>>>(d, n, nt, r); else if (mode == 1) kfloor<1><<<blocks, 256>>>(d, n, nt, r); else kfloor<2><<<blocks, 256>>>(d, n, nt, r);
+      cudaDeviceSynchronize();
+    }
+    cudaMemcpy(hr, r, sizeof(long long) * 2 * blocks, cudaMemcpyDeviceToHost);
+    double sfl = 0; for (int b = 0; b < blocks; b++) sfl += (double)hr[2 * b];
+    printf("blocks %3d tick floor mode %d: %.1f cycles/tick\n", blocks, mode, sfl / blocks / nt);
+  }
   for (int blocks : {1, 592}) {
-    for (int v : {5, 9, 14, 15}) {
+    for (int v : {5, 14, 16, 17}) {
       for (int rep = 0; rep < 2; rep++) {
         switch (v) {
           case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
@@ -347,6 +390,8 @@ int main() {
           case 9: k<9><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 14: k<14><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 15: k<15><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 16: k<16><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 17: k<17><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
         }
         cudaDeviceSynchronize();
       }
