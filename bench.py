@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance")
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shim-leg", action="store_true", help="skip the reference-host-with-GPU-shim point (64 files through oracle/_ref/jref_gpu)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the 1-utterance / 16-utterance points and the short DNN-HMM leg")
     ap.add_argument("--cpu-sample-utts", type=int, default=0)
     return ap.parse_args()
@@ -481,6 +482,48 @@ def rooflines(r, world):
     return roof, scoring
 
 
+def shim_leg(name: str, n_files: int, T: int, ahead: int) -> dict:
+    """What the real host gets: oracle/_ref/jref_gpu = the unmodified Julius host with the pass-1 beam externs linked to
+    the GPU shim, decoding a list of n_files utterances one utterance per call, and with the shim's
+    decode-ahead over the same list (JB200_FILELIST).  Rates are frames / time between PASS1_BEGIN and PASS1_END."""
+    from julius_b200 import workload
+    jref_gpu = os.path.join(ROOT, "oracle", "_ref", "jref_gpu")
+    if not os.path.exists(jref_gpu) or name in workload.DNN_SHAPES:
+        return {"unavailable": "oracle/_ref/jref_gpu not built" if not os.path.exists(jref_gpu) else "GMM workloads only"}
+    m = workload.synth_model(name)
+    tmp = tempfile.mkdtemp(prefix="jb200_shim_")
+    feats = workload.sample_inputs(name, m, n_files, T, seed=31337)
+    files = []
+    for i, x in enumerate(feats):
+        fn = os.path.join(tmp, f"u{i}.mfc")
+        workload.write_input(name, fn, x)
+        files.append(fn)
+    lst = os.path.join(tmp, "files.lst")
+    with open(lst, "w") as f:
+        f.write("\n".join(files) + "\n")
+    out = {"files": n_files, "frames_per_file": T}
+    for tag, env_extra in (("one_utterance_per_call", {}), ("decode_ahead", {"JB200_FILELIST": lst, "JB200_AHEAD": str(ahead)})):
+        env = dict(os.environ, JREF_QUIET="1", **env_extra)
+        args = [jref_gpu, "-dump", "/dev/null"] + workload.ref_args(name)
+        p = subprocess.run(args, input="\n".join(files) + "\n", text=True, capture_output=True, env=env)
+        kv = {}
+        for line in p.stdout.splitlines():
+            if line.startswith("JREF_SUMMARY"):
+                kv = dict(x.split("=") for x in line.split()[1:])
+        if not kv:
+            out[tag] = {"failed": (p.stdout[-300:] + p.stderr[-300:])}
+            continue
+        sec = float(kv["decode_sec"])
+        out[tag] = {"decode_sec": sec, "frames_per_s": int(kv["frames"]) / sec, "ms_per_file": 1000.0 * sec / max(int(kv["utts"]), 1)}
+    if "frames_per_s" in out.get("decode_ahead", {}) and "frames_per_s" in out.get("one_utterance_per_call", {}):
+        out["speedup"] = out["decode_ahead"]["frames_per_s"] / out["one_utterance_per_call"]["frames_per_s"]
+        out["ahead"] = ahead
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return out
+
+
 def product_main(a):
     import torch
     import torch.distributed as dist
@@ -507,6 +550,11 @@ def product_main(a):
             q = measure_workload(ctx, a.workload, b, T, 3, 2, mode=a.mode, want_e2e=True)
             extra[tag] = {"utterances": b, "frames_per_utt": T, "ms_device": q["dev_ms"] / q["steps"], "ms_e2e": q["e2e_ms"] / q["steps"],
                           "frames_per_s_e2e": b * T * q["steps"] / (q["e2e_ms"] / 1000.0)}
+        if not a.no_shim_leg:
+            try:
+                extra["host_shim"] = shim_leg(a.workload, 64, T, 32)
+            except Exception as e:
+                extra["host_shim"] = {"failed": str(e)}
         # K2 on the driver's record: a short leg of the DNN-HMM workload (BASELINE configs[3]) unless it is the headline
         if a.workload != "dnn20k":
             from julius_b200 import workload as _w

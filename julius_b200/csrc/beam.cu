@@ -379,6 +379,7 @@ __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, con
   int next_x = 0, wait = 0;
   unsigned ticks = 0, stalls = 0;
   if (lane == 0 && extract > 0) outs[0] = __ldcg(A + 1);
+  unsigned long long nxt = __ldcg(A + n);
   while (true) {
     // (1) children pair of the hole
     ulonglong2 pr = make_ulonglong2(sent, sent);
@@ -404,8 +405,11 @@ __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, con
         const int ms = n - next_x;
         const int ln = next_x & (NL - 1);
         bool blocks = act && ((int)lane == ln);
-        const int dh = 31 - __clz(max(slot, 1)), dms = 31 - __clz(ms);
-        blocks = blocks || (act && dms >= dh && (ms >> (dms - dh)) == slot);
+        // a tail slot holding a loser is never a hole and never decides anything (loser cut), and a loser stays a loser
+        if (!(MAXHEAP && hval(nxt) < lose_below)) {
+          const int dh = 31 - __clz(max(slot, 1)), dms = 31 - __clz(ms);
+          blocks = blocks || (act && dms >= dh && (ms >> (dms - dh)) == slot);
+        }
         if (!__any_sync(FULL, blocks)) {
           if ((int)lane == ln) {
             s = __ldcg(A + ms);
@@ -413,6 +417,7 @@ __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, con
             my_x = next_x; act = true; slot = 1; cur = 1;
           }
           next_x++; wait = 2;
+          nxt = __ldcg(A + (n - next_x));                 // the next tail slot's content (every lane: a broadcast)
         } else stalls++;
       }
     }
@@ -506,7 +511,8 @@ __device__ void heap_extract_fast(unsigned long long *A, const int n, const int 
       if (!__isShared(A)) heap_extract_pipe_global<MAXHEAP>(A, n, extract, lose_below, outv, maxt, ticks, stalls);
       else
       if (single_thread == 2) heap_extract_pipe_warp<MAXHEAP>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
-      else heap_extract_pipe_warp4<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
+      else if (single_thread == 3) heap_extract_pipe_warp4<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
+      else heap_extract_pipe_warp6<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
       if (threadIdx.x == 0) {
         atomicAdd(stats + 1, (unsigned long long)ticks); atomicAdd(stats + 2, (unsigned long long)extract);
         atomicAdd(stats + 3, (unsigned long long)stalls);
@@ -1389,6 +1395,9 @@ struct jb200_decoder {
   int atoms_per_frame = 64;
   BeamParams P{};
   std::vector<void *> dev_allocs;
+  // read-only tables shared by all utterances (tree, LM, inter-word table, bigram memo) sit in ONE allocation so that a
+  // single L2 access-policy window can keep them resident while the per-utterance work areas stream through
+  char *arena = nullptr; size_t arena_size = 0, arena_used = 0; bool l2_window = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5]{};
   // batch buffers
@@ -1410,12 +1419,32 @@ struct jb200_decoder {
   bool grammar = false;
 };
 
+// from the shared-table arena when it has room, else an allocation of its own
+static void *arena_take(jb200_decoder *d, size_t bytes) {
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (!d->arena || d->arena_used + need > d->arena_size) return nullptr;
+  void *p = d->arena + d->arena_used;
+  d->arena_used += need;
+  return p;
+}
 template <typename Tp>
 static int dev_upload(jb200_decoder *d, const Tp *src, size_t n, const Tp **dst) {
-  Tp *p = nullptr;
-  JB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+  Tp *p = static_cast<Tp *>(arena_take(d, std::max<size_t>(n, 1) * sizeof(Tp)));
+  if (!p) {
+    JB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+    d->dev_allocs.push_back(p);
+  }
   if (n) JB_CUDA(cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
-  d->dev_allocs.push_back(p);
+  *dst = p;
+  return JB200_OK;
+}
+template <typename Tp>
+static int dev_alloc_shared(jb200_decoder *d, size_t n, Tp **dst) {
+  Tp *p = static_cast<Tp *>(arena_take(d, std::max<size_t>(n, 1) * sizeof(Tp)));
+  if (!p) {
+    JB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+    d->dev_allocs.push_back(p);
+  }
   *dst = p;
   return JB200_OK;
 }
@@ -1431,6 +1460,7 @@ static int dev_alloc(jb200_decoder *d, size_t n, Tp **dst) {
 extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
   if (!d) return;
   cudaSetDevice(d->device);
+  if (d->l2_window) cudaCtxResetPersistingL2Cache();
   for (void *p : d->dev_allocs) cudaFree(p);
   if (d->h_results) cudaFreeHost(d->h_results);
   if (d->h_atoms) cudaFreeHost(d->h_atoms);
@@ -1476,6 +1506,15 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
 
   BeamParams &P = d->P;
   const int n = t->n_nodes;
+  {
+    // shared read-only tables: nodes 32 B, arcs 8 B, context table, inter-word table, bigram memo, LM arrays (+ slack)
+    const int lmc_bits_est = (t->n_words >= 65535 || t->n_scword >= 65535) ? 0 : 21;
+    size_t est = (size_t)n * 32 + (size_t)t->n_arcs * 8 * 3 + (size_t)t->n_rset * (t->n_ctx + 1) * 4 + (size_t)t->n_words * 32 +
+                 (size_t)t->n_words * std::max(t->n_iso, 1) * (grammar ? 1 : 4) + ((size_t)8 << lmc_bits_est) +
+                 (size_t)t->lm_nvocab * 16 + (size_t)t->lm_nbigram * 8 + (size_t)(t->n_iso + t->n_shared + t->n_fscore + t->n_scword) * 16 + (4u << 20);
+    if (getenv("JB200_NO_ARENA") == nullptr && cudaMalloc(&d->arena, est) == cudaSuccess) { d->arena_size = est; d->dev_allocs.push_back(d->arena); }
+    else { d->arena = nullptr; cudaGetLastError(); }
+  }
   // node records
   std::vector<NodeRec> nodes(n);
   for (int i = 0; i < n; i++) {
@@ -1570,7 +1609,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     const int *d_iso_word = nullptr;
     TRY(dev_upload(d, t->iso_word, (size_t)t->n_iso, &d_iso_word));
     float *iw = nullptr;
-    TRY(dev_alloc(d, (size_t)t->n_words * std::max(t->n_iso, 1), &iw));
+    TRY(dev_alloc_shared(d, (size_t)t->n_words * std::max(t->n_iso, 1), &iw));
     P.iw = iw;
     const long long tot = grammar ? 0 : (long long)t->n_words * t->n_iso;     // grammar mode reads cp_allowed instead
     if (tot > 0) {
@@ -1626,14 +1665,14 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     if (bits > 26) bits = 26;
     P.lmc_bits = bits; P.lmc = nullptr;
     if (bits > 0) {
-      TRY(dev_alloc(d, (size_t)1 << bits, &P.lmc));
+      TRY(dev_alloc_shared(d, (size_t)1 << bits, &P.lmc));
       TRYC(cudaMemsetAsync(P.lmc, 0xff, sizeof(unsigned long long) << bits, d->stream));
     }
   }
   P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   P.no_closed = getenv("JB200_NO_CLOSED_FORM") ? atoi(getenv("JB200_NO_CLOSED_FORM")) : 0;   // 1: always replay the extraction loop
-  P.heap_single = getenv("JB200_HEAP_SINGLE") ? atoi(getenv("JB200_HEAP_SINGLE")) : 0;   // 1: the single-thread replay, 2: the branchy pipelined loop (A/B timing)
+  P.heap_single = getenv("JB200_HEAP_SINGLE") ? atoi(getenv("JB200_HEAP_SINGLE")) : 0;   // 1: the single-thread replay, 2: the readable pipelined loop, 3: the C++ form of the shipped loop (A/B timing)
   {
     size_t tot = (size_t)max_utts * n;
     fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(P.slots, tot);
@@ -1667,6 +1706,25 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BEAM_THREADS, d->smem_bytes));
     TRYC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
     d->resident = per_sm * sms;
+  }
+  // keep the shared tables in L2: with one distinct utterance per resident block the per-utterance work areas alone exceed
+  // L2 several times over, and every eviction of a tree / LM line is a DRAM round trip inside a dependent chain
+  if (d->arena && d->arena_used > 0 && getenv("JB200_NO_L2_WINDOW") == nullptr) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      const size_t win = std::min<size_t>(d->arena_used, (size_t)prop.accessPolicyMaxWindowSize);
+      const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, win);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = d->arena;
+        av.accessPolicyWindow.num_bytes = win;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        d->l2_window = (cudaStreamSetAttribute(d->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess);
+      }
+    }
+    cudaGetLastError();
   }
   TRYC(cudaStreamSynchronize(d->stream));
 #undef TRY

@@ -232,19 +232,77 @@ __device__ __forceinline__ void heap_extract_pipe_warp4(unsigned long long *A, c
   ticks_out = ticks; stalls_out = stalls;
 }
 
-// ---- a leaner bookkeeping of the same schedule (candidate for the shipped loop; FLAGS as above).  Every lane knows the
-// extractions it owns (my_x = lane, lane+16, ...), where their tail slot and their output entry live, and has the tail
-// slot's content prefetched one round (32 ticks) ahead -- a loser stays a loser, and a non-loser only sends the start
-// through the ancestor vote, where s is read afresh anyway.  A start then costs one compare, one ballot and a handful of
-// predicated updates instead of recomputing all of it from next_x.
+// ---- the step in PTX.  One warp issues about one instruction every two cycles however little they depend on each other,
+// so once the shared-memory round trip is covered (~64 cycles with the compare and the address select: "tick floor" in
+// tools/ubench/heapx.cu) a tick costs its instruction count.  The step below is 24 instructions; the address arithmetic
+// that does not need the loaded pair is issued in the load's shadow.  act: 0/1.
+template <bool MAXHEAP>
+__device__ __forceinline__ void hp_step(unsigned &cur, unsigned &slot, unsigned &act, const unsigned s_lo, const unsigned s_hi,
+                                        const float lose_dn, const unsigned out_w, const unsigned nhb, const unsigned capa,
+                                        const unsigned root) {
+#define HP_STEP_HEAD                                                                                                     \
+      "{\n\t"                                                                                                            \
+      ".reg .pred pa, pr, ps, pq, pg;\n\t"                                                                               \
+      ".reg .b32 x0, x1, y0, y1, clo, chi, plo, phi, b2, b2r, sr;\n\t"                                                   \
+      ".reg .f32 fx, fy, fs, cv, thr;\n\t"                                                                               \
+      "setp.ne.u32 pa, %2, 0;\n\t"                                                                                       \
+      "ld.shared.v4.u32 {x0, x1, y0, y1}, [%0];\n\t"                                                                     \
+      "mad.lo.u32 b2, %0, 2, %7;\n\t"             /* 2*cur - hb: the pair below the LEFT child */                        \
+      "add.u32 b2r, b2, 16;\n\t"                                                                                         \
+      "min.u32 b2, b2, %8;\n\t"                                                                                          \
+      "min.u32 b2r, b2r, %8;\n\t"                                                                                        \
+      "add.u32 sr, %0, 8;\n\t"                    /* slot of the right child (the left child's is cur) */                \
+      "setp.eq.and.u32 pq, %1, %9, pa;\n\t"       /* this lane fills the root: its value is the next output */          \
+      "mov.b32 fs, %3;\n\t"
+#define HP_STEP_TAIL                                                                                                     \
+      "selp.b32 clo, y0, x0, pr;\n\t"                                                                                    \
+      "selp.b32 chi, y1, x1, pr;\n\t"                                                                                    \
+      "selp.b32 plo, %3, clo, ps;\n\t"                                                                                   \
+      "selp.b32 phi, %4, chi, ps;\n\t"                                                                                   \
+      "@pa st.shared.v2.u32 [%1], {plo, phi};\n\t"                                                                       \
+      "@pq st.shared.v2.u32 [%6], {plo, phi};\n\t"                                                                       \
+      "selp.u32 %1, sr, %0, pr;\n\t"              /* the hole moves to the chosen child ... */                           \
+      "selp.u32 %0, b2r, b2, pr;\n\t"             /* ... whose children pair is next */                                  \
+      "not.pred ps, ps;\n\t"                                                                                             \
+      "and.pred pg, pa, ps;\n\t"                                                                                         \
+      "selp.u32 %2, 1, 0, pg;\n\t"                                                                                       \
+      "}\n"
+  if (MAXHEAP)
+    asm volatile(HP_STEP_HEAD
+                 "max.f32 thr, fs, %5;\n\t"       /* stop test "s >= c || c < lose_below" == "c <= max(s, nextdown(lose_below))" */
+                 "mov.b32 fx, x0;\n\t"
+                 "mov.b32 fy, y0;\n\t"
+                 "setp.lt.f32 pr, fx, fy;\n\t"    /* "child < child+1": the right child only when strictly larger */
+                 "max.f32 cv, fx, fy;\n\t"
+                 "setp.le.f32 ps, cv, thr;\n\t"
+                 HP_STEP_TAIL
+                 : "+r"(cur), "+r"(slot), "+r"(act)
+                 : "r"(s_lo), "r"(s_hi), "f"(lose_dn), "r"(out_w), "r"(nhb), "r"(capa), "r"(root)
+                 : "memory");
+  else
+    asm volatile(HP_STEP_HEAD
+                 "mov.b32 fx, x0;\n\t"
+                 "mov.b32 fy, y0;\n\t"
+                 "setp.gt.f32 pr, fx, fy;\n\t"    /* "child > child+1": the right child only when strictly smaller */
+                 "min.f32 cv, fx, fy;\n\t"
+                 "setp.ge.f32 ps, cv, fs;\n\t"    /* "s <= c" */
+                 HP_STEP_TAIL
+                 : "+r"(cur), "+r"(slot), "+r"(act)
+                 : "r"(s_lo), "r"(s_hi), "f"(lose_dn), "r"(out_w), "r"(nhb), "r"(capa), "r"(root)
+                 : "memory");
+#undef HP_STEP_HEAD
+#undef HP_STEP_TAIL
+}
+
 template <bool MAXHEAP, int FLAGS>
-__device__ __forceinline__ void heap_extract_pipe_warp5(unsigned long long *A, const int n, const int extract, const float lose_below,
+__device__ __forceinline__ void heap_extract_pipe_warp6(unsigned long long *A, const int n, const int extract, const float lose_below,
                                                         unsigned long long *outs, const int maxt, const unsigned lane,
                                                         unsigned &ticks_out, unsigned &stalls_out) {
   constexpr int NL = 16;
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned hb = hp_smem_u32(A);
   const unsigned ob = hp_smem_u32(outs);
+  const unsigned nhb = 0u - hb;
   const unsigned sent = MAXHEAP ? 0xff800000u : 0x7f800000u;
   const unsigned capa = hb + (((unsigned)(maxt >> 1) + 1u) << 4);
   const unsigned root = hb + 8u;
@@ -254,61 +312,38 @@ __device__ __forceinline__ void heap_extract_pipe_warp5(unsigned long long *A, c
     b = (lose_below > 0.0f) ? b - 1u : (lose_below < 0.0f) ? b + 1u : 0x80000001u;
     lose_dn = __uint_as_float(b);
   }
-  bool act = false;
-  unsigned slot = capa, cur = capa;
+  unsigned act = 0u, slot = capa, cur = capa;
   unsigned s_lo = sent, s_hi = 0u;
-  int my_x = (lane < NL) ? (int)lane : 0x7fffffff;         // the next extraction this lane owns
-  unsigned my_ma = hb + ((unsigned)(n - (int)lane) << 3);   // its tail slot
-  unsigned my_out = ob + ((lane + 1u) << 3);                // where its root write goes: outs[my_x + 1]
-  unsigned out_w = ob;                                      // the same for the extraction in flight
-  unsigned nxt_lo = sent, nxt_hi = 0u;
-  hp_lds_one_if(my_x < extract, my_ma, nxt_lo, nxt_hi);
+  unsigned out_w = ob;
   int next_x = 0, wait = 0;
   unsigned ticks = 0, stalls = 0;
+  unsigned nxt_lo, nxt_hi;
+  hp_lds_one(hb + ((unsigned)n << 3), nxt_lo, nxt_hi);
   if (lane == 0 && extract > 0) outs[0] = A[1];
   while (true) {
-    unsigned x0, x1, y0, y1;
-    hp_lds_pair(cur, x0, x1, y0, y1);
-    {
-      const unsigned base2 = (cur << 1) - hb;
-      const float sv = __uint_as_float(s_lo), xv = __uint_as_float(x0), yv = __uint_as_float(y0);
-      const float thr = MAXHEAP ? fmaxf(sv, lose_dn) : sv;
-      const bool right = MAXHEAP ? (xv < yv) : (xv > yv);
-      const float cv = MAXHEAP ? fmaxf(xv, yv) : fminf(xv, yv);
-      const bool stop = MAXHEAP ? (cv <= thr) : (cv >= thr);
-      const unsigned c_lo = right ? y0 : x0, c_hi = right ? y1 : x1;
-      const unsigned p_lo = stop ? s_lo : c_lo, p_hi = stop ? s_hi : c_hi;
-      hp_sts_one_if(act, slot, p_lo, p_hi);
-      hp_sts_one_if(act && slot == root, out_w, p_lo, p_hi);
-      slot = cur + (right ? 8u : 0u);
-      cur = min(base2 + (right ? 16u : 0u), capa);
-      act = act && !stop;
-    }
+    hp_step<MAXHEAP>(cur, slot, act, s_lo, s_hi, lose_dn, out_w, nhb, capa, root);
     if (--wait <= 0) {
       if (next_x >= extract) {
-        if (!__any_sync(FULL, act)) break;
+        if (!__any_sync(FULL, act != 0u)) break;
       } else {
-        const bool mine = (my_x == next_x);
-        const bool careful = mine && !(MAXHEAP && (__uint_as_float(nxt_lo) < lose_below));
+        const unsigned ms = (unsigned)(n - next_x);
         bool ok = true;
-        if (__any_sync(FULL, careful)) {                                     // rare with the loser cut
-          const unsigned ms = (unsigned)(n - next_x);
+        if (!(MAXHEAP && (__uint_as_float(nxt_lo) < lose_below))) {          // rare with the loser cut
           const unsigned h = (slot - hb) >> 3;
           const int dh = 31 - __clz(h), dms = 31 - __clz(ms);
-          ok = !__any_sync(FULL, act && dms >= dh && (ms >> (dms - dh)) == h);
+          ok = !__any_sync(FULL, act != 0u && dms >= dh && (ms >> (dms - dh)) == h);
         }
         if (ok) {
-          hp_lds_one_if(mine, my_ma, s_lo, s_hi);                            // s = A[m]
-          hp_sts_one_if(mine, my_ma, sent, 0u);                              // slot m leaves the heap
-          out_w = mine ? my_out : out_w;
+          const bool mine = (lane == ((unsigned)next_x & (NL - 1)));
+          const unsigned ma = hb + (ms << 3);
+          hp_lds_one_if(mine, ma, s_lo, s_hi);                               // s = A[m]
+          hp_sts_one_if(mine, ma, sent, 0u);                                 // slot m leaves the heap
+          next_x++;
+          out_w = mine ? ob + ((unsigned)next_x << 3) : out_w;               // outs[x + 1]
+          hp_lds_one(ma - 8u, nxt_lo, nxt_hi);                               // the next tail slot's content
+          act = mine ? 1u : act;
           slot = mine ? root : slot;
           cur = mine ? hb + 16u : cur;
-          act = act || mine;
-          my_x += mine ? NL : 0;
-          my_ma -= mine ? (unsigned)(NL * 8) : 0u;
-          my_out += mine ? (unsigned)(NL * 8) : 0u;
-          hp_lds_one_if(mine && my_x < extract, my_ma, nxt_lo, nxt_hi);      // next round's tail content
-          next_x++;
           wait = 2;
         } else stalls++;
       }

@@ -24,16 +24,33 @@
 #include <julius/juliuslib.h>
 #include "jb200_model.h"
 #include "jb200_dl.h"
+#include <time.h>
+
+static double shim_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 extern int jb200_flatten(PROCESS_AM *am, RecogProcess *r, jb200_blob *b);   /* jb200_export.c */
+
+/* one decoded utterance, copied out of the decoder (decode-ahead cache, and the current utterance) */
+typedef struct {
+  unsigned long long hash;   /* of the feature vectors it was decoded from */
+  int n_frames;
+  jb200_utt_result u;
+  jb200_atom *atoms;         /* [u.n_atoms] */
+  int32_t *words;            /* [u.n_words] */
+} ShimResult;
 
 typedef struct {
   RecogProcess *r;
   jb200_blob blob;
   jb200_gmm_desc gd; jb200_dnn_desc dd; jb200_tree_desc td;
   jb200_gmm *gmm; jb200_dnn *dnn; jb200_decoder *dec;
-  int max_frames;
+  int max_frames, max_utts;
   boolean ok;            /* last decode succeeded */
+  ShimResult cur;        /* result of the utterance being finished */
+  /* decode-ahead over a file list (JB200_FILELIST = the list given to -filelist, JB200_AHEAD = how many files a batch) */
+  char **files; int n_files, next_file;   /* next_file: index of the utterance the host will finish next */
+  ShimResult *ahead; int n_ahead, ahead_first;
+  long n_from_cache, n_single;
 } Shim;
 
 static jb200_api g_api;
@@ -41,12 +58,14 @@ static int g_api_loaded = 0;
 static Shim g_shim[8];
 static int g_nshim = 0;
 
-static Shim *shim_for(RecogProcess *r, int frames) {
+static Shim *shim_for2(RecogProcess *r, int frames, int utts);
+static Shim *shim_for(RecogProcess *r, int frames) { return shim_for2(r, frames, 1); }
+static Shim *shim_for2(RecogProcess *r, int frames, int utts) {
   int i, rc;
   Shim *s = NULL;
   const char *mode = getenv("JB200_GMM_MODE");
   for (i = 0; i < g_nshim; i++) if (g_shim[i].r == r) s = &g_shim[i];
-  if (s && frames <= s->max_frames) return s;
+  if (s && frames <= s->max_frames && utts <= s->max_utts) return s;
   if (!g_api_loaded) { if (jb200_api_load(&g_api, (void *)&shim_for) != 0) return NULL; g_api_loaded = 1; }
   if (s == NULL) {
     if (g_nshim >= 8) { jlog("ERROR: jb200: too many recognition instances\n"); return NULL; }
@@ -82,16 +101,18 @@ static Shim *shim_for(RecogProcess *r, int frames) {
   /* (re)create the decoder for the longest utterance seen so far: the old one (device work areas, pinned host
    * buffers) is released first, and the capacity is recorded only once the new one exists */
   {
-    const int want = frames < 4096 ? 4096 : frames + frames / 2;
-    if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; s->max_frames = 0; }
-    rc = g_api.decoder_create(&s->td, s->gmm, 1, want, &s->dec);
+    int want = frames < 4096 ? 4096 : frames + frames / 2;
+    const int want_utts = utts > s->max_utts ? utts : (s->max_utts > 0 ? s->max_utts : 1);
+    if (want < s->max_frames) want = s->max_frames;
+    if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; s->max_frames = 0; s->max_utts = 0; }
+    rc = g_api.decoder_create(&s->td, s->gmm, want_utts, want, &s->dec);
     if (rc == 0 && s->dnn) rc = g_api.decoder_attach_dnn(s->dec, s->dnn);
     if (rc != 0) {
       jlog("ERROR: jb200: %s\n", g_api.last_error());
       if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; }
       return NULL;
     }
-    s->max_frames = want;
+    s->max_frames = want; s->max_utts = want_utts;
   }
   return s;
 }
@@ -121,14 +142,127 @@ boolean get_back_trellis_proceed(int t, HTK_Param *param, RecogProcess *r, boole
   return TRUE;
 }
 
-void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
+/* ---- results: copies that outlive the decoder's buffers -------------------------------------------------------- */
+static void result_free(ShimResult *x) { free(x->atoms); free(x->words); memset(x, 0, sizeof(*x)); }
+
+static int result_copy(ShimResult *x, const jb200_utt_result *u, const jb200_atom *atoms, const int32_t *words) {
+  result_free(x);
+  x->u = *u;
+  x->atoms = (jb200_atom *)malloc(sizeof(jb200_atom) * (size_t)(u->n_atoms > 0 ? u->n_atoms : 1));
+  x->words = (int32_t *)malloc(sizeof(int32_t) * (size_t)(u->n_words > 0 ? u->n_words : 1));
+  if (!x->atoms || !x->words) { result_free(x); return -1; }
+  if (u->n_atoms > 0) memcpy(x->atoms, atoms + u->atom_offset, sizeof(jb200_atom) * (size_t)u->n_atoms);
+  if (u->n_words > 0) memcpy(x->words, words + u->word_offset, sizeof(int32_t) * (size_t)u->n_words);
+  x->u.atom_offset = 0; x->u.word_offset = 0;
+  return 0;
+}
+
+static unsigned long long feat_hash(const float *x, size_t n) {      /* FNV-1a over the bit patterns */
+  const unsigned char *b = (const unsigned char *)x;
+  unsigned long long h = 1469598103934665603ULL;
+  size_t i;
+  for (i = 0; i < n * sizeof(float); i++) { h ^= b[i]; h *= 1099511628211ULL; }
+  return h;
+}
+
+/* ---- decode-ahead: the host hands over one utterance at a time (pass1.c:220-254), one utterance occupies one of several
+ * hundred resident thread blocks.  With JB200_FILELIST = the list the host reads its HTK parameter files from, the shim
+ * reads the next JB200_AHEAD files itself, decodes them in ONE batch, and answers the host's following utterances from
+ * the cache -- but only when the vectors the host presents hash to what was decoded (any host-side processing of the
+ * input, or a list that does not match, silently falls back to the one-utterance path). */
+static float *read_htk_param(const char *fn, int want_dim, int *n_frames) {
+  FILE *fp = fopen(fn, "rb");
+  unsigned char h[12];
+  unsigned int ns, ssize;
+  float *x; size_t i, n;
+  if (!fp) return NULL;
+  if (fread(h, 1, 12, fp) != 12) { fclose(fp); return NULL; }
+  ns = ((unsigned)h[0] << 24) | ((unsigned)h[1] << 16) | ((unsigned)h[2] << 8) | h[3];
+  ssize = ((unsigned)h[8] << 8) | h[9];
+  if (ns < 1 || ns > 32767 || ssize != (unsigned)want_dim * 4u) { fclose(fp); return NULL; }
+  n = (size_t)ns * want_dim;
+  x = (float *)malloc(sizeof(float) * n);
+  if (!x || fread(x, 4, n, fp) != n) { free(x); fclose(fp); return NULL; }
+  fclose(fp);
+  for (i = 0; i < n; i++) {                                           /* big-endian floats (rdparam.c:83-187) */
+    unsigned char *b = (unsigned char *)(x + i), t;
+    t = b[0]; b[0] = b[3]; b[3] = t; t = b[1]; b[1] = b[2]; b[2] = t;
+  }
+  *n_frames = (int)ns;
+  return x;
+}
+
+static void load_filelist(Shim *s) {
+  const char *fn = getenv("JB200_FILELIST");
+  char line[4096]; FILE *fp;
+  s->n_files = 0; s->files = NULL;
+  if (!fn || !(fp = fopen(fn, "r"))) return;
+  while (fgets(line, sizeof(line), fp)) {
+    size_t L = strlen(line);
+    while (L > 0 && (line[L - 1] == '\n' || line[L - 1] == '\r' || line[L - 1] == ' ')) line[--L] = '\0';
+    if (L == 0 || line[0] == '#') continue;
+    s->files = (char **)realloc(s->files, sizeof(char *) * (size_t)(s->n_files + 1));
+    s->files[s->n_files++] = strdup(line);
+  }
+  fclose(fp);
+  jlog("STAT: jb200: decode-ahead over %d files of %s\n", s->n_files, fn);
+}
+
+static void ahead_clear(Shim *s) {
+  int i;
+  for (i = 0; i < s->n_ahead; i++) result_free(&s->ahead[i]);
+  free(s->ahead); s->ahead = NULL; s->n_ahead = 0;
+}
+
+/* decode files [first, first+k) in one batch; leaves whatever could be decoded in the cache */
+static void ahead_fill(Shim *s, int first) {
+  const char *e = getenv("JB200_AHEAD");
+  int k = e ? atoi(e) : 32, i, n = 0, total = 0, D = s->gd.dim;
+  float **xs; int *T; float *cat; int32_t *off;
   const jb200_utt_result *u; const jb200_atom *a; const int32_t *w;
+  Shim *s2;
+  const double t0 = shim_now(); double t1 = t0, t2 = t0, t3 = t0;
+  ahead_clear(s);
+  if (k < 2) return;
+  if (first + k > s->n_files) k = s->n_files - first;
+  if (k < 2) return;
+  xs = (float **)calloc((size_t)k, sizeof(float *)); T = (int *)calloc((size_t)k, sizeof(int));
+  for (i = 0; i < k; i++) {
+    xs[i] = read_htk_param(s->files[first + i], D, &T[i]);
+    if (!xs[i]) break;
+    total += T[i]; n++;
+  }
+  t1 = shim_now();
+  if (n >= 2 && (s2 = shim_for2(s->r, total, n)) != NULL) {
+    t2 = shim_now();
+    cat = (float *)malloc(sizeof(float) * (size_t)total * D);
+    off = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1));
+    off[0] = 0;
+    for (i = 0; i < n; i++) { memcpy(cat + (size_t)off[i] * D, xs[i], sizeof(float) * (size_t)T[i] * D); off[i + 1] = off[i] + T[i]; }
+    if (g_api.decode_batch_host(s->dec, cat, off, n) == 0 && g_api.decoder_results(s->dec, &u, &a, &w) == 0) {
+      t3 = shim_now();
+      s->ahead = (ShimResult *)calloc((size_t)n, sizeof(ShimResult));
+      s->n_ahead = n; s->ahead_first = first;
+      if (getenv("JB200_SHIM_VERBOSE")) { printf("JB200_SHIM batch first=%d n=%d frames=%d read=%.3fs decoder=%.3fs decode=%.3fs\n", first, n, total, t1 - t0, t2 - t1, t3 - t2); fflush(stdout); }
+      for (i = 0; i < n; i++) {
+        result_copy(&s->ahead[i], &u[i], a, w);
+        s->ahead[i].hash = feat_hash(xs[i], (size_t)T[i] * D);
+        s->ahead[i].n_frames = T[i];
+      }
+    } else jlog("WARNING: jb200: decode-ahead batch failed (%s); continuing one utterance at a time\n", g_api.last_error());
+    free(cat); free(off);
+  }
+  for (i = 0; i < k; i++) free(xs[i]);
+  free(xs); free(T);
+}
+
+void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
   TRELLIS_ATOM **idx;
   const int T = param->samplenum;
   Shim *s = shim_for(r, T);
-  int i, t, D;
-  int32_t off[2];
+  int i, t, D, utt;
   float *in;
+  unsigned long long h;
   if (s == NULL) return;
   s->ok = FALSE;
   if (T < 1 || param->is_outprob || param->veclen < s->gd.dim) return;       /* refused at _init already */
@@ -136,15 +270,33 @@ void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
   in = (float *)malloc(sizeof(float) * (size_t)T * D);
   if (in == NULL) { jlog("ERROR: jb200: out of memory\n"); return; }
   for (t = 0; t < T; t++) memcpy(in + (size_t)t * D, param->parvec[t], sizeof(float) * D);
-  off[0] = 0; off[1] = T;
-  if (g_api.decode_batch_host(s->dec, in, off, 1) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); free(in); return; }
+  /* answered by the decode-ahead cache? */
+  utt = s->next_file++;
+  if (s->files == NULL && s->n_files == 0 && getenv("JB200_FILELIST")) { load_filelist(s); if (s->n_files == 0) s->n_files = -1; }
+  if (s->n_files > 0 && utt < s->n_files) {
+    if (!(s->n_ahead > 0 && utt >= s->ahead_first && utt < s->ahead_first + s->n_ahead)) ahead_fill(s, utt);
+    if (s->n_ahead > 0 && utt >= s->ahead_first && utt < s->ahead_first + s->n_ahead) {
+      ShimResult *c = &s->ahead[utt - s->ahead_first];
+      h = feat_hash(in, (size_t)T * D);
+      if (c->atoms != NULL && c->n_frames == T && c->hash == h && result_copy(&s->cur, &c->u, c->atoms, c->words) == 0) {
+        s->ok = TRUE; s->n_from_cache++;
+        if (getenv("JB200_SHIM_VERBOSE")) { printf("JB200_SHIM utt=%d from_cache\n", utt); fflush(stdout); }
+      }
+    }
+  }
+  if (!s->ok) {
+    const jb200_utt_result *u; const jb200_atom *a; const int32_t *w;
+    int32_t off[2];
+    off[0] = 0; off[1] = T;
+    if (g_api.decode_batch_host(s->dec, in, off, 1) != 0 || g_api.decoder_results(s->dec, &u, &a, &w) != 0 ||
+        result_copy(&s->cur, u, a, w) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); free(in); return; }
+    s->ok = TRUE; s->n_single++;
+  }
   free(in);
-  s->ok = TRUE;
-  if (g_api.decoder_results(s->dec, &u, &a, &w) != 0) return;
-  if (u->overflow) { jlog("ERROR: jb200: device work area overflow (code %d); pass 1 result dropped\n", u->overflow); return; }
-  a += u->atom_offset;
-  idx = (TRELLIS_ATOM **)malloc(sizeof(void *) * (u->n_atoms + 1));
-  for (i = 0; i < u->n_atoms; i++) {
+  if (s->cur.u.overflow) { jlog("ERROR: jb200: device work area overflow (code %d); pass 1 result dropped\n", s->cur.u.overflow); s->ok = FALSE; return; }
+  idx = (TRELLIS_ATOM **)malloc(sizeof(void *) * (size_t)(s->cur.u.n_atoms + 1));
+  for (i = 0; i < s->cur.u.n_atoms; i++) {
+    const jb200_atom *a = s->cur.atoms;
     TRELLIS_ATOM *tre = bt_new(r->backtrellis);
     tre->wid = (WORD_ID)a[i].wid;
     tre->begintime = (short)a[i].begintime; tre->endtime = (short)a[i].endtime;
@@ -165,17 +317,17 @@ void finalize_1st_pass(RecogProcess *r, int len) {
   bt->framelen = len;
   bt_relocate_rw(bt);
   bt_sort_rw(bt);
-  if (bt->num == NULL || s == NULL || !s->ok || g_api.decoder_results(s->dec, &u, &a, &w) != 0) {
+  if (bt->num == NULL || s == NULL || !s->ok) {
     if (bt->framelen > 0) jlog("WARNING: %02d %s: input processed, but no survived word found\n", r->config->id, r->config->name);
     r->result.status = J_RESULT_STATUS_FAIL;
     return;
   }
+  u = &s->cur.u; a = s->cur.atoms; w = s->cur.words;
   if (u->status != 0) {
     jlog("WARNING: %02d %s: no tail silence word survived on the last frame, search failed\n", r->config->id, r->config->name);
     r->result.status = J_RESULT_STATUS_FAIL;
     return;
   }
-  w += u->word_offset;
   /* what find_1pass_result publishes (beam.c:497-517) */
   r->result.status = J_RESULT_STATUS_SUCCESS;
   r->result.num_frame = len;
@@ -184,11 +336,9 @@ void finalize_1st_pass(RecogProcess *r, int len) {
   r->result.pass1.score = u->score;
   {
     /* total LM score along the best path = sum of lscore of its atoms (trace_backptr, beam.c:253-301) */
-    LOGPROB lsum = 0.0; int k, last_time = len - 1, best = -1;
-    a += u->atom_offset;
+    LOGPROB lsum = 0.0; int k, best = -1;
     for (k = u->n_atoms - 1; k >= 0 && best < 0; k--)
       if (a[k].wid == (int)r->lm->winfo->tail_silwid && a[k].backscore == u->score) best = k;
-    (void)last_time;
     for (k = best; k >= 0; k = a[k].last) { lsum += a[k].lscore; if (a[k].begintime <= 0) break; }
     r->result.pass1.score_lm = lsum;
     r->result.pass1.score_am = u->score - lsum;
@@ -209,6 +359,8 @@ void fsbeam_free(FSBeam *d) {
     if (s->dec) { g_api.decoder_destroy(s->dec); s->dec = NULL; }
     if (s->dnn) { g_api.dnn_destroy(s->dnn); s->dnn = NULL; }
     if (s->gmm) { g_api.gmm_destroy(s->gmm); s->gmm = NULL; }
+    if (s->n_files > 0) jlog("STAT: jb200: %ld utterances answered from decode-ahead batches, %ld decoded singly\n", s->n_from_cache, s->n_single);
+    ahead_clear(s); result_free(&s->cur);
     jb200_blob_free(&s->blob);
     s->r = NULL; s->max_frames = 0; s->ok = FALSE;
   }

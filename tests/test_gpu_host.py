@@ -100,3 +100,35 @@ def test_calcmix_hook_equals_gprune_none(tmp_path):
         ok, why = atoms_equal(v.atoms, u.atoms)
         assert ok, why
         assert u.words == v.words and np.float32(u.score) == np.float32(v.score)
+
+
+def test_beam_shim_decode_ahead_over_a_file_list(tmp_path):
+    """The stock host hands the shim one utterance at a time.  With JB200_FILELIST naming the same list the host reads,
+    the shim decodes the next files in one GPU batch and answers the host's following utterances from that batch --
+    only when the vectors the host presents hash to what was decoded.  Same trellis and pass-1 result as the stock
+    host, every utterance after the first batch answered from the cache."""
+    from oracle import ffi
+    g, d, files = _prepare("small_b100", tmp_path)
+    files = files + files                      # 2 x the golden utterances: a list longer than one batch
+    lst = os.path.join(d, "files.lst")
+    with open(lst, "w") as f:
+        f.write("\n".join(files) + "\n")
+    dump, out = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], binary=ffi.JREF_GPU,
+                            env_extra={"JB200_FILELIST": lst, "JB200_AHEAD": "3", "JB200_SHIM_VERBOSE": "1"})
+    utts = refdump.load_refdump(dump)
+    assert len(utts) == len(files)
+    for u, ref in zip(utts, g.utts + g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.status == ref.status and u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+    assert out.count("from_cache") == len(files)
+    assert out.count("JB200_SHIM batch") == (len(files) + 2) // 3
+    # a list that does not match what the host reads is harmless: everything is decoded singly, same result
+    bad = os.path.join(d, "bad.lst")
+    with open(bad, "w") as f:
+        f.write("\n".join(reversed(files)) + "\n")
+    dump2, out2 = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], binary=ffi.JREF_GPU, dump="bad.jrf",
+                              env_extra={"JB200_FILELIST": bad, "JB200_AHEAD": "3", "JB200_SHIM_VERBOSE": "1"})
+    for u, ref in zip(refdump.load_refdump(dump2), g.utts + g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why

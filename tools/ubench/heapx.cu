@@ -31,7 +31,8 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
   return r;
 }
 
-// V: 9 = the pipelined warp replay of heap_pipe.cuh, readable form; 14 = the shipped form (15: without __syncwarp);
+// V: 9 = the pipelined warp replay of heap_pipe.cuh, readable form; 14 = lock-step form in C++ (15: without __syncwarp);
+// 18 = the shipped form, step in PTX (19: without __syncwarp);
 // single-thread variants: 0 = round 1's loop; 1 = outv in shared memory; 2 = no loser-cut test; 3 = non-volatile (sinkable) load;
 //    4 = one level per loop trip (no ping-pong unroll); 5 = plain load whose result is also consumed on the
 //    exit path (ptxas must issue it ahead of the stop test); 6 = 5 + both grandchild pairs requested one level
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(256, 4) k(const unsigned long long *init, int 
       if (V == 9) jb200::heap_extract_pipe_warp<true>(A, n, extract, lose_below, outg + (size_t)blockIdx.x * 1024, MAXT, threadIdx.x, ticks, stalls);
       else if (V == 14) jb200::heap_extract_pipe_warp4<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
       else if (V == 15) jb200::heap_extract_pipe_warp4<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
-      else if (V == 16) jb200::heap_extract_pipe_warp5<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
-      else jb200::heap_extract_pipe_warp5<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else if (V == 18) jb200::heap_extract_pipe_warp6<true, 0>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
+      else jb200::heap_extract_pipe_warp6<true, 1>(A, n, extract, lose_below, outs, MAXT, threadIdx.x, ticks, stalls);
       long long t1 = clock64();
       if (threadIdx.x == 0) { res[blockIdx.x * 2] = t1 - t0; res[blockIdx.x * 2 + 1] = ticks; }
     }
@@ -375,7 +376,7 @@ int main() {
     printf("blocks %3d tick floor mode %d: %.1f cycles/tick\n", blocks, mode, sfl / blocks / nt);
   }
   for (int blocks : {1, 592}) {
-    for (int v : {5, 14, 16, 17}) {
+    for (int v : {5, 14, 18, 19}) {
       for (int rep = 0; rep < 2; rep++) {
         switch (v) {
           case 0: k<0><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
@@ -390,8 +391,8 @@ int main() {
           case 9: k<9><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 14: k<14><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
           case 15: k<15><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
-          case 16: k<16><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
-          case 17: k<17><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 18: k<18><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
+          case 19: k<19><<<blocks, 256>>>(d, n, extract, lose_below, o, r); break;
         }
         cudaDeviceSynchronize();
       }
