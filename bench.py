@@ -171,14 +171,15 @@ def ref_procs(info: dict | None = None) -> int:
     return max(1, min(info["usable_threads"], physical))
 
 
-def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int, seed: int, warm_frames: int = 100):
+def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int, seed: int, warm_frames: int = 100,
+                  binary: str = "jref"):
     """n_procs independent reference processes, each loading the model once and decoding one short warm-up
     utterance followed by n_timed utterances of n_frames frames.  Returns per-process
     (timed frames, timed decode seconds); decode time = between PASS1_BEGIN and PASS1_END of each utterance."""
     from julius_b200 import workload
-    jref = os.path.join(ROOT, "oracle", "_ref", "jref")
+    jref = os.path.join(ROOT, "oracle", "_ref", binary)
     if not os.path.exists(jref):
-        raise RuntimeError("oracle/_ref/jref is missing (built by __graft_entry__.build() where /root/reference exists)")
+        raise RuntimeError(f"oracle/_ref/{binary} is missing (built by __graft_entry__.build() where /root/reference exists)")
     m = workload.synth_model(workload_name)
     tmp = tempfile.mkdtemp(prefix="jb200_ref_")
     rng = np.random.default_rng(seed)
@@ -192,14 +193,16 @@ def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int,
             workload.write_input(workload_name, fn, x)
             files.append(fn)
         args = [jref, "-dump", "/dev/null"] + workload.ref_args(workload_name)
-        p = subprocess.Popen(args, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+        p = subprocess.Popen(args, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
         p.stdin.write("\n".join(files) + "\n")
         p.stdin.close()
         procs.append(p)
     per_proc = []
+    last_out = ""
     for p in procs:
         out = p.stdout.read()
         p.wait()
+        last_out = out
         fr, sec = 0, 0.0
         for line in out.splitlines():
             if line.startswith("JREF_UTT"):
@@ -212,7 +215,7 @@ def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int,
         os.remove(os.path.join(tmp, f))
     os.rmdir(tmp)
     if not per_proc:
-        raise RuntimeError("reference produced no timing lines")
+        raise RuntimeError("reference produced no timing lines: " + last_out[-400:].replace("\n", " | "))
     return per_proc
 
 
@@ -243,6 +246,18 @@ def reference_measure(workload_name: str, n_timed: int, n_frames: int, seed: int
             "tried": tried, "timed_sec_slowest_process": (n_timed * n_frames * best["nproc"]) / best["frames_per_s"],
             "cpu_count": info["cpu_count"], "affinity": info["affinity"], "cgroup_quota": info["cgroup_quota"],
             "threads_per_core": info["threads_per_core"]}
+
+
+def reference_cuda_dnn(workload_name: str, n_frames: int) -> dict:
+    """The only GPU code the reference ships: its CUDA DNN forward (libsent/src/phmm/calc_dnn_cuda.cu, per-frame GEMV
+    kernels, 15 launches and two PCIe copies a frame), built by oracle/Makefile as oracle/_ref/jref_cuda.
+    Whole pass 1 (CUDA DNN scoring + the host's beam), 1 process and one process per usable core sharing the GPU."""
+    out = {}
+    for tag, n in (("1_process", 1), ("per_core", ref_procs())):
+        pp = run_reference(workload_name, n, 1, n_frames, 777, binary="jref_cuda")
+        out[tag] = {"nproc": n, "frames_per_s": sum(f for f, _ in pp) / max(s for _, s in pp),
+                    "frames_per_s_per_process": float(np.median([f / s for f, s in pp]))}
+    return out
 
 
 def reference_main(a):
@@ -400,6 +415,7 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
     res = dec.results()
     phase = dec.phase_cycles(min(B, 64)).mean(0)
     n_ok = sum(1 for r in res if r["status"] == 0 and r["overflow"] == 0)
+    failures = [{"utt": i, "status": r["status"], "overflow": r["overflow"]} for i, r in enumerate(res) if r["status"] != 0 or r["overflow"] != 0][:8]
     counts = dec.frame_counts(0, T)
     hs = dec.heap_stats()
 
@@ -410,7 +426,7 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
     out = dict(name=name, ds=ds, use_dnn=use_dnn, B=B, T=T, S=S, M_total=M_total, D=D, resident=resident, steps=steps,
                dev_ms=dev_ms_max, wall_ms=wall_ms_max, e2e_ms=e2e_ms_max, h2d=h2d, d2h=d2h, launches=int(launches),
                score_ms=float(np.mean(score_ms)), beam_ms=float(np.mean(beam_ms)), clocks=clocks, phase=phase,
-               n_ok=n_ok, n_res=len(res), tokens_per_frame=float(counts[:, 1].mean()), created_per_frame=float(counts[:, 0].mean()),
+               n_ok=n_ok, n_res=len(res), failures=failures, tokens_per_frame=float(counts[:, 1].mean()), created_per_frame=float(counts[:, 0].mean()),
                heap=hs, misspec=dec.misspeculations(), beam_width=int(ds.tree.beam_width), multipath=int(ds.tree.multipath))
     if use_dnn:
         out["dnn_flops_per_frame"] = dnn_flops_per_frame
@@ -503,7 +519,7 @@ def shim_leg(name: str, n_files: int, T: int, ahead: int) -> dict:
         f.write("\n".join(files) + "\n")
     out = {"files": n_files, "frames_per_file": T}
     for tag, env_extra in (("one_utterance_per_call", {}), ("decode_ahead", {"JB200_FILELIST": lst, "JB200_AHEAD": str(ahead)})):
-        env = dict(os.environ, JREF_QUIET="1", **env_extra)
+        env = dict(os.environ, JREF_QUIET="1", JB200_SHIM_VERBOSE="1", **env_extra)
         args = [jref_gpu, "-dump", "/dev/null"] + workload.ref_args(name)
         p = subprocess.run(args, input="\n".join(files) + "\n", text=True, capture_output=True, env=env)
         kv = {}
@@ -515,6 +531,9 @@ def shim_leg(name: str, n_files: int, T: int, ahead: int) -> dict:
             continue
         sec = float(kv["decode_sec"])
         out[tag] = {"decode_sec": sec, "frames_per_s": int(kv["frames"]) / sec, "ms_per_file": 1000.0 * sec / max(int(kv["utts"]), 1)}
+        if env_extra:
+            out[tag]["answered_from_batches"] = p.stdout.count("from_cache")
+            out[tag]["batches"] = [ln.split("batch ", 1)[1] for ln in p.stdout.splitlines() if ln.startswith("JB200_SHIM batch")]
     if "frames_per_s" in out.get("decode_ahead", {}) and "frames_per_s" in out.get("one_utterance_per_call", {}):
         out["speedup"] = out["decode_ahead"]["frames_per_s"] / out["one_utterance_per_call"]["frames_per_s"]
         out["ahead"] = ahead
@@ -534,6 +553,13 @@ def product_main(a):
     if world != a.gpus:
         if world == 1 and a.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    host_shim = None
+    if world == 1 and not a.no_extra_legs and not a.no_shim_leg:
+        # the host-with-shim point runs other processes on the same GPU: before this process creates its CUDA context
+        try:
+            host_shim = shim_leg(a.workload, 64, a.frames, 32)
+        except Exception as e:
+            host_shim = {"failed": str(e)}
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
@@ -550,11 +576,8 @@ def product_main(a):
             q = measure_workload(ctx, a.workload, b, T, 3, 2, mode=a.mode, want_e2e=True)
             extra[tag] = {"utterances": b, "frames_per_utt": T, "ms_device": q["dev_ms"] / q["steps"], "ms_e2e": q["e2e_ms"] / q["steps"],
                           "frames_per_s_e2e": b * T * q["steps"] / (q["e2e_ms"] / 1000.0)}
-        if not a.no_shim_leg:
-            try:
-                extra["host_shim"] = shim_leg(a.workload, 64, T, 32)
-            except Exception as e:
-                extra["host_shim"] = {"failed": str(e)}
+        if host_shim is not None:
+            extra["host_shim"] = host_shim
         # K2 on the driver's record: a short leg of the DNN-HMM workload (BASELINE configs[3]) unless it is the headline
         if a.workload != "dnn20k":
             from julius_b200 import workload as _w
@@ -586,9 +609,14 @@ def product_main(a):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"] // a.steps, "d2h_bytes_per_step": r["d2h"] // a.steps,
                     "ms_per_step": r["e2e_ms"] / a.steps},
             "gpu_launches": r["launches"],
-            "decoded_ok": f"{r['n_ok']}/{r['n_res']}", "heap_misspeculations": r["misspec"], "clocks": r["clocks"],
+            "decoded_ok": f"{r['n_ok']}/{r['n_res']}", "decode_failures": r["failures"], "heap_misspeculations": r["misspec"], "clocks": r["clocks"],
         }
         line.update(extra)
+        if world == 1 and not a.no_cpu_baseline and r["use_dnn"] and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "jref_cuda")):
+            try:
+                line["reference_cuda_dnn"] = reference_cuda_dnn(a.workload, T)
+            except Exception as e:
+                line["reference_cuda_dnn"] = {"failed": str(e)[-300:]}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 upp = a.cpu_sample_utts or 1

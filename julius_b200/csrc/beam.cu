@@ -109,7 +109,7 @@ struct BeamParams {
   int maxt, maxc, maxw, maxbits;
   // token sets too large for shared memory (wide beams on large trees): the heap-select array lives in global memory
   // ([n_utts][maxt+4] entries) and shared memory only holds the closed form's sort area (sort_cap 8-byte keys)
-  unsigned long long *heap_g; int sort_cap;
+  unsigned long long *heap_g; int sort_cap, qcap;      // qcap: 8-byte entries of the shared-memory area in front of offs (>= sort_cap)
   // grammar (DFA) mode, appended so that the offsets of everything above stay what the N-gram kernels were built with
   const uint8_t *cp_allowed; const int *init_node; const float *init_lscore; int n_init; float penalty1;
 };
@@ -172,16 +172,23 @@ __device__ __forceinline__ float max_successor_prob(const BeamParams &p, int las
   return v;
 }
 
+// a state score is read once per utterance-frame (the row belongs to this utterance alone): JB200_STREAM_HINTS marks
+// these and the last reads of the candidate records evict-first, so that they displace less of what is re-used
+#ifdef JB200_STREAM_HINTS
+#define JB_LD_ROW(p_) __ldcs(p_)
+#else
+#define JB_LD_ROW(p_) __ldg(p_)
+#endif
 // outprob_cd, outprob.c:286-400, evaluated on demand from the frame's state-score row
 __device__ float cdset_score(const BeamParams &p, const float *__restrict__ row, int c) {
   const int b0 = __ldg(p.cd_off + c), n_in = __ldg(p.cd_off + c + 1) - b0;
   if (p.iwcd_method == JB200_IWCD_AVG) {
     float sum = 0.0f; int j = 0;
-    for (int i = 0; i < n_in; i++) { float v = __ldg(row + __ldg(p.cd_states + b0 + i)); if (v > JB200_LOG_ZERO) { sum += v; j++; } }
+    for (int i = 0; i < n_in; i++) { float v = JB_LD_ROW(row + __ldg(p.cd_states + b0 + i)); if (v > JB200_LOG_ZERO) { sum += v; j++; } }
     return sum / (float)j;
   } else if (p.iwcd_method == JB200_IWCD_MAX) {
     float mx = JB200_LOG_ZERO;
-    for (int i = 0; i < n_in; i++) { float v = __ldg(row + __ldg(p.cd_states + b0 + i)); if (mx < v) mx = v; }
+    for (int i = 0; i < n_in; i++) { float v = JB_LD_ROW(row + __ldg(p.cd_states + b0 + i)); if (mx < v) mx = v; }
     return mx;
   }
   const int maxn = p.iwcd_nbest;
@@ -190,7 +197,7 @@ __device__ float cdset_score(const BeamParams &p, const float *__restrict__ row,
     // largest down (outprob.c:313-318): three registers instead of an indexed array in local memory
     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY; int n = 0;
     for (int i = 0; i < n_in; i++) {
-      const float v = __ldg(row + __ldg(p.cd_states + b0 + i));
+      const float v = JB_LD_ROW(row + __ldg(p.cd_states + b0 + i));
       if (v <= JB200_LOG_ZERO) continue;
       n++;
       if (v > m0) { m2 = m1; m1 = m0; m0 = v; }
@@ -206,7 +213,7 @@ __device__ float cdset_score(const BeamParams &p, const float *__restrict__ row,
   }
   float mp[CD_NMAX + 1]; int n = 0;
   for (int i = 0; i < n_in; i++) {
-    float prob = __ldg(row + __ldg(p.cd_states + b0 + i));
+    float prob = JB_LD_ROW(row + __ldg(p.cd_states + b0 + i));
     if (prob <= JB200_LOG_ZERO) continue;
     if (n == 0 || prob <= mp[n - 1]) {
       if (n == maxn) continue;
@@ -231,11 +238,11 @@ __device__ float cdset_score(const BeamParams &p, const float *__restrict__ row,
 // outprob_style, outprob_style.c:354-494 with the context resolution tabulated on the host
 __device__ __forceinline__ float outprob_style(const BeamParams &p, const float *__restrict__ row, int out, int last_wid) {
   const int style = (unsigned)out >> 28, ref = out & 0x0fffffff;
-  if (style == JB200_AS_STATE) return __ldg(row + ref);
+  if (style == JB200_AS_STATE) return JB_LD_ROW(row + ref);
   if (style == JB200_AS_LSET) return cdset_score(p, row, ref);
   const int col = (last_wid < 0) ? p.n_ctx : __ldg(p.word_ctx + last_wid);
   const int r = __ldg(p.rset_ctx + (size_t)ref * (p.n_ctx + 1) + col);
-  if (r >= 0) return __ldg(row + r);
+  if (r >= 0) return JB_LD_ROW(row + r);
   return cdset_score(p, row, -r - 1);
 }
 
@@ -365,25 +372,50 @@ __device__ __forceinline__ ulonglong2 ldcg_pair(const unsigned long long *p) {
   const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
   return make_ulonglong2(((unsigned long long)v.y << 32) | v.x, ((unsigned long long)v.w << 32) | v.z);
 }
+// Shared-memory copies that go with a global-memory heap (write-through, so global stays the truth):
+//   top  : slots [0, cs) -- the top levels of the tree, which every extraction walks;
+//   tail : slots [tail_first, tail_first + tail_n) -- where the extractions take their s from.
+// Deeper levels are touched only by the few sifts that follow winners all the way down.
+struct HeapCache {
+  unsigned long long *top; int cs;
+  unsigned long long *tail; int tail_first, tail_n;
+};
+
 template <bool MAXHEAP>
 __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, const int extract, const float lose_below,
-                                         unsigned long long *outs, const int maxt, unsigned &ticks_out, unsigned &stalls_out) {
+                                         unsigned long long *outs, const int maxt, const HeapCache hc,
+                                         unsigned &ticks_out, unsigned &stalls_out) {
   constexpr int NL = 16;
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long sent = MAXHEAP ? 0xff800000ull : 0x7f800000ull;
   const int cap = (maxt >> 1) + 1;                          // pair (maxt+2, maxt+3): always sentinels
+  auto load_slot = [&](int i) -> unsigned long long {
+    if (i < hc.cs) return hc.top[i];
+    if (i >= hc.tail_first && i < hc.tail_first + hc.tail_n) return hc.tail[i - hc.tail_first];
+    return __ldcg(A + i);
+  };
+  auto store_slot = [&](int i, unsigned long long v) {
+    __stcg(A + i, v);
+    if (i < hc.cs) hc.top[i] = v;
+    else if (i >= hc.tail_first && i < hc.tail_first + hc.tail_n) hc.tail[i - hc.tail_first] = v;
+  };
   bool act = false;
   int slot = 0, cur = cap, my_x = 0;                        // hole index, pair index of its children (slots 2cur, 2cur+1)
   unsigned long long s = sent;
   int next_x = 0, wait = 0;
   unsigned ticks = 0, stalls = 0;
-  if (lane == 0 && extract > 0) outs[0] = __ldcg(A + 1);
-  unsigned long long nxt = __ldcg(A + n);
+  if (lane == 0 && extract > 0) outs[0] = load_slot(1);
+  unsigned long long nxt = load_slot(n);
   while (true) {
     // (1) children pair of the hole
     ulonglong2 pr = make_ulonglong2(sent, sent);
-    if (act) pr = ldcg_pair(A + 2 * cur);
+    if (act) {
+      const int i = 2 * cur;
+      if (i + 1 < hc.cs) pr = *reinterpret_cast<const ulonglong2 *>(hc.top + i);
+      else if (i >= hc.tail_first && i + 1 < hc.tail_first + hc.tail_n) pr = make_ulonglong2(hc.tail[i - hc.tail_first], hc.tail[i + 1 - hc.tail_first]);
+      else pr = ldcg_pair(A + i);
+    }
     // (2) fill the hole, move one level down or end
     if (act) {
       const float xv = hval(pr.x), yv = hval(pr.y), sv = hval(s);
@@ -392,7 +424,7 @@ __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, con
       const float cv = hval(c);
       const bool stop = hstop<MAXHEAP>(sv, cv) || (MAXHEAP && cv < lose_below);
       const unsigned long long put = stop ? s : c;
-      __stcg(A + slot, put);
+      store_slot(slot, put);
       if (slot == 1) outs[my_x + 1] = put;
       if (stop) act = false;
       else { slot = 2 * cur + (right ? 1 : 0); cur = min(slot, cap); }
@@ -412,12 +444,12 @@ __device__ void heap_extract_pipe_global(unsigned long long *A, const int n, con
         }
         if (!__any_sync(FULL, blocks)) {
           if ((int)lane == ln) {
-            s = __ldcg(A + ms);
-            __stcg(A + ms, sent);
+            s = load_slot(ms);
+            store_slot(ms, sent);
             my_x = next_x; act = true; slot = 1; cur = 1;
           }
           next_x++; wait = 2;
-          nxt = __ldcg(A + (n - next_x));                 // the next tail slot's content (every lane: a broadcast)
+          nxt = load_slot(n - next_x);                    // the next tail slot's content (every lane: a broadcast)
         } else stalls++;
       }
     }
@@ -502,13 +534,47 @@ __device__ __forceinline__ unsigned heap_pick(unsigned x0, unsigned y0, unsigned
 template <bool MAXHEAP>
 __device__ void heap_extract_fast(unsigned long long *A, const int n, const int extract, const float lose_below,
                                   unsigned long long *outv, const int maxt, unsigned long long *stats,
-                                  const SlotClear *idle_work = nullptr, const int single_thread = 0) {
+                                  const SlotClear *idle_work = nullptr, const int single_thread = 0,
+                                  unsigned long long *gcache = nullptr, const int gcache_n = 0,
+                                  unsigned long long *gtail = nullptr, const int gtail_n = 0) {
+  HeapCache hc{nullptr, 0, nullptr, 0, 0};
+  if (!__isShared(A) && gcache && n + 8 <= gcache_n && single_thread != 1) {
+    // global-memory heap that fits the shared-memory area as a whole (select #1 of a multipath frame, and the smaller
+    // frames of a wide beam): replay on a shared-memory copy at shared-memory speed, then write the arrangement back
+    const int lmaxt = (gcache_n - 4) & ~1;
+    for (int i = threadIdx.x; i <= n; i += BEAM_THREADS) gcache[i] = A[i];
+    heap_pad_sentinels<MAXHEAP>(gcache, n, lmaxt);
+    __syncthreads();
+    if (threadIdx.x >= 32 && idle_work) idle_work->run((int)threadIdx.x - 32, BEAM_THREADS - 32);
+    if (threadIdx.x < 32) {
+      unsigned ticks, stalls;
+      heap_extract_pipe_warp6<MAXHEAP, 0>(gcache, n, extract, lose_below, outv, lmaxt, threadIdx.x, ticks, stalls);
+      if (threadIdx.x == 0) {
+        atomicAdd(stats + 1, (unsigned long long)ticks); atomicAdd(stats + 2, (unsigned long long)extract);
+        atomicAdd(stats + 3, (unsigned long long)stalls);
+      }
+    }
+    __syncthreads();
+    for (int i = 1 + threadIdx.x; i <= n; i += BEAM_THREADS) A[i] = gcache[i];
+    __syncthreads();
+    return;
+  }
+  if (!__isShared(A) && gcache && gcache_n > 0) {
+    // global-memory heap: copy its top levels and its tail into shared memory first (all threads)
+    hc.top = gcache; hc.cs = min(gcache_n, maxt + 4) & ~1;
+    for (int i = threadIdx.x; i < hc.cs; i += BEAM_THREADS) gcache[i] = A[i];
+    if (gtail && gtail_n >= extract) {
+      hc.tail = gtail; hc.tail_first = n - extract + 1; hc.tail_n = extract;
+      for (int i = threadIdx.x; i < extract; i += BEAM_THREADS) gtail[i] = A[hc.tail_first + i];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x >= 32 && idle_work) idle_work->run((int)threadIdx.x - 32, BEAM_THREADS - 32);
   if (single_thread != 1 || !__isShared(A)) {
     // warp 0: up to 16 extractions in flight, one tree level per tick each (heap_pipe.cuh)
     if (threadIdx.x < 32) {
       unsigned ticks, stalls;
-      if (!__isShared(A)) heap_extract_pipe_global<MAXHEAP>(A, n, extract, lose_below, outv, maxt, ticks, stalls);
+      if (!__isShared(A)) heap_extract_pipe_global<MAXHEAP>(A, n, extract, lose_below, outv, maxt, hc, ticks, stalls);
       else
       if (single_thread == 2) heap_extract_pipe_warp<MAXHEAP>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
       else if (single_thread == 3) heap_extract_pipe_warp4<MAXHEAP, 0>(A, n, extract, lose_below, outv, maxt, threadIdx.x, ticks, stalls);
@@ -828,14 +894,15 @@ extern __shared__ __align__(16) unsigned char beam_smem[];
 // "exists") and bestkey = (score, seq 0), so later arrivals only replace its content when strictly better.
 template <bool MAXHEAP>
 __device__ __forceinline__ int select_exact(unsigned long long *heap, int n, int need, int *ordn, unsigned long long *outv, int maxt,
-                                            unsigned long long *stats, const int heap_single) {
+                                            unsigned long long *stats, const int heap_single,
+                                            unsigned long long *gcache, const int gcache_n, unsigned long long *gtail, const int gtail_n) {
   // sort_token_no_order (beam.c:1492-1520) replayed in full; the extracted roots are put back into the
   // tail slots where the in-place algorithm leaves them (k-th extracted at slot n-k).  Returns the first
   // survivor's slot.
   const int extract = MAXHEAP ? need : n - need;
   heap_pad_sentinels<MAXHEAP>(heap, n, maxt);
   heap_build<MAXHEAP>(heap, n);
-  heap_extract_fast<MAXHEAP>(heap, n, extract, -INFINITY, outv, maxt, stats, nullptr, heap_single);
+  heap_extract_fast<MAXHEAP>(heap, n, extract, -INFINITY, outv, maxt, stats, nullptr, heap_single, gcache, gcache_n, gtail, gtail_n);
   for (int k = threadIdx.x; k < extract; k += BEAM_THREADS) heap[n - k] = outv[k];
   __syncthreads();
   const int start = MAXHEAP ? n - need : 0;
@@ -855,8 +922,14 @@ beam_kernel_mp(const BeamParams p) {
   // shared memory: [heap (MAXT+4 entries) | offs], or, when the heap lives in global memory, [sort area | offs]
   unsigned long long *const smem_q = reinterpret_cast<unsigned long long *>(beam_smem);
   unsigned long long *heap = p.heap_g ? p.heap_g + (size_t)blockIdx.x * (MAXT + 4) : smem_q;
-  int *offs = reinterpret_cast<int *>(smem_q + (p.heap_g ? p.sort_cap : MAXT + 4));
+  int *offs = reinterpret_cast<int *>(smem_q + (p.heap_g ? p.qcap : MAXT + 4));
   int *hist = offs;                                                               // reused by select #2
+  // global-memory heap: the area in front of offs doubles as the replay's copy of the heap's top levels, and a copy of
+  // the tail slots follows offs
+  unsigned long long *const gq = p.heap_g ? smem_q : nullptr;
+  const int gqn = p.heap_g ? p.qcap : 0;
+  unsigned long long *const gtail = p.heap_g ? reinterpret_cast<unsigned long long *>(offs + 2 * (p.beam + 2)) : nullptr;
+  const int gtn = p.heap_g ? p.beam + 1 : 0;
   __shared__ int s_warp[NWARP + 1];
   __shared__ int s_E, s_natoms, s_ns, s_cur, s_overflow, s_found, s_cf[2];
   __shared__ unsigned s_pmaxkey, s_hmaxkey, s_losekey;
@@ -1046,8 +1119,8 @@ beam_kernel_mp(const BeamParams p) {
         for (int k = tid; k < ns_a; k += BEAM_THREADS) ordn[k] = k;
       } else {
         ns_a = need;
-        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single);
-        else select_exact<false>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single);
+        if (need < ncre_a - need) select_exact<true>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single, gq, gqn, gtail, gtn);
+        else select_exact<false>(heap, ncre_a, need, ordn, outv, MAXT, p.misspec_counter, p.heap_single, gq, gqn, gtail, gtn);
       }
     }
     __syncthreads();
@@ -1325,7 +1398,7 @@ beam_kernel_mp(const BeamParams p) {
         if (!closed) {
           heap_pad_sentinels<true>(heap, ncre, MAXT);
           __syncthreads();
-          heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, p.no_closed ? &sc : nullptr, p.heap_single);
+          heap_extract_fast<true>(heap, ncre, need, lose_below, outv, MAXT, p.misspec_counter, p.no_closed ? &sc : nullptr, p.heap_single, gq, gqn, gtail, gtn);
           for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(outv[need - 1 - k] >> 32);
         }
       } else {
@@ -1334,7 +1407,7 @@ beam_kernel_mp(const BeamParams p) {
         heap_build<false>(heap, ncre); PROF_MARK(7);
         const SlotClear sc{tn, ncre, slots};
         slots_clean = true;
-        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter, &sc, p.heap_single);
+        heap_extract_fast<false>(heap, ncre, rest, -INFINITY, outv, MAXT, p.misspec_counter, &sc, p.heap_single, gq, gqn, gtail, gtn);
         for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(heap[k + 1] >> 32);
       }
     }
@@ -1395,8 +1468,8 @@ struct jb200_decoder {
   int atoms_per_frame = 64;
   BeamParams P{};
   std::vector<void *> dev_allocs;
-  // read-only tables shared by all utterances (tree, LM, inter-word table, bigram memo) sit in ONE allocation so that a
-  // single L2 access-policy window can keep them resident while the per-utterance work areas stream through
+  // read-only tables shared by all utterances (tree, LM, inter-word table, bigram memo) sit in ONE allocation (one
+  // contiguous range for an optional L2 access-policy window, see jb200_decoder_create)
   char *arena = nullptr; size_t arena_size = 0, arena_used = 0; bool l2_window = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5]{};
@@ -1633,12 +1706,19 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   smem_limit -= 2048;                                       // static shared variables of the kernels
   bool heap_global = (size_t)(maxt + 4) * 8 + offs_bytes > (size_t)smem_limit / 2;   // would leave one block per SM
   if (const char *e = getenv("JB200_HEAP_GLOBAL")) heap_global = atoi(e) != 0;
-  P.heap_g = nullptr; P.sort_cap = 0;
+  P.heap_g = nullptr; P.sort_cap = 0; P.qcap = 0;
   if (heap_global) {
     if (!getenv("JB200_MAXT")) maxt = std::min(65000, (std::max(maxt, 9 * t->beam_width + t->n_start) + 3) & ~3);
     int sc = 1024; while (sc < 2 * t->beam_width && sc < 16384) sc <<= 1;       // candidates = beam + one histogram bin
-    if ((size_t)sc * 8 + offs_bytes > (size_t)smem_limit) { set_error("beam width %d needs more shared memory than the device has", t->beam_width); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
+    const size_t tail_bytes = (size_t)(t->beam_width + 2) * 8;                   // the replay's copy of the tail slots
+    if ((size_t)sc * 8 + offs_bytes + tail_bytes > (size_t)smem_limit) { set_error("beam width %d needs more shared memory than the device has", t->beam_width); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
     P.sort_cap = sc;
+    // what is left of shared memory holds the top levels of the heap during a replay (one block per SM: the replay is all
+    // that matters at these beam widths); JB200_HEAP_CACHE=0 keeps only the sort area (two blocks per SM)
+    int qc = sc;
+    if (!getenv("JB200_HEAP_CACHE") || atoi(getenv("JB200_HEAP_CACHE")) != 0)
+      while ((size_t)qc * 2 * 8 + offs_bytes + tail_bytes <= (size_t)smem_limit && qc * 2 <= ((maxt + 4) | 1023) + 1) qc <<= 1;
+    P.qcap = qc;
     TRY(dev_alloc(d, (size_t)max_utts * (maxt + 4), &P.heap_g));
   }
   P.maxt = maxt; P.maxc = 4 * maxt; P.maxw = t->beam_width + 1;
@@ -1697,7 +1777,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_atoms, sizeof(jb200_atom) * (size_t)d->atoms_cap));
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
-  d->smem_bytes = (heap_global ? (size_t)P.sort_cap * 8 : (size_t)(maxt + 4) * 8) + offs_bytes;
+  d->smem_bytes = (heap_global ? (size_t)P.qcap * 8 + (size_t)(t->beam_width + 2) * 8 : (size_t)(maxt + 4) * 8) + offs_bytes;
   d->grammar = grammar;
   const void *kern = grammar ? (const void *)beam_kernel_grammar : P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
   TRYC(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_bytes));
@@ -1707,9 +1787,10 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     TRYC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
     d->resident = per_sm * sms;
   }
-  // keep the shared tables in L2: with one distinct utterance per resident block the per-utterance work areas alone exceed
-  // L2 several times over, and every eviction of a tree / LM line is a DRAM round trip inside a dependent chain
-  if (d->arena && d->arena_used > 0 && getenv("JB200_NO_L2_WINDOW") == nullptr) {
+  // Opt-in (JB200_L2_WINDOW=1): an L2 access-policy window that keeps the shared tables resident (persisting hits, streaming
+  // misses).  Measured on the 20k-word workload with 592 distinct utterances: 1.194 M frames/s with the window, 1.224 M
+  // without -- the set-aside costs the per-utterance work areas more than it saves on tree / LM lines -- so it is off.
+  if (d->arena && d->arena_used > 0 && getenv("JB200_L2_WINDOW") != nullptr && atoi(getenv("JB200_L2_WINDOW")) != 0) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, d->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
       const size_t win = std::min<size_t>(d->arena_used, (size_t)prop.accessPolicyMaxWindowSize);
