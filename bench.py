@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--utts", type=int, default=0, help="utterances per GPU per step (0 = one resident wave)")
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance")
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--pipe-frames", type=int, default=-1,
+                    help="GMM workloads: frames per time slice of the batch pipeline (scoring of slice c+1 beside the beam of slice c); "
+                         "0 = off (one launch per batch), -1 = the default of this build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shim-leg", action="store_true", help="skip the reference-host-with-GPU-shim point (64 files through oracle/_ref/jref_gpu)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the 1-utterance / 16-utterance points and the short DNN-HMM leg")
@@ -314,7 +317,10 @@ def fp32_peak():
     return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 figure in MEASURED_PEAKS.json)"
 
 
-def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True, n_batches=2, seed0=100):
+PIPE_FRAMES_DEFAULT = 0       # set from the round's measurements, see DESIGN.md K3/K1 "batch pipeline"
+
+
+def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True, n_batches=2, seed0=100, pipe_frames=0):
     """W warm-up + K timed steps of one workload at B utterances x T frames per GPU; returns the measured figures.
     ctx: dict(rank, local, world, device, torch, dist)."""
     torch, dist = ctx["torch"], ctx["dist"]
@@ -339,11 +345,15 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
     probe = capi.Decoder(ds, am, max_utts=1, max_frames=8)
     resident = max(1, probe.resident_utts())       # one resident wave of thread blocks
     probe.close()
+    pipe = 0 if use_dnn else max(0, pipe_frames)
     if not B:
-        B = resident
+        # the pipeline needs room for one scoring thread block beside the beam's on every SM: 3/4 of a resident wave
+        B = (resident * 3) // 4 if pipe else resident
     dec = capi.Decoder(ds, am, max_utts=B, max_frames=B * T)
     if use_dnn:
         dec.attach_dnn(dnn)
+    if pipe:
+        dec.set_pipeline(pipe)
 
     # synthetic input, different per rank and batch: B DISTINCT utterances per batch (no tiling: identical blocks would
     # walk the same tree nodes, bigram rows and memo entries in step and flatter the cache hit rates)
@@ -382,12 +392,14 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
     t_wall0 = time.time()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    score_ms, beam_ms = [], []
+    score_ms, beam_ms, busy_ms = [], [], []
     for k in range(steps):
         step_device(k)
         capi._check(lib.jb200_decoder_sync_timing(dec.handle_ptr()), "sync_timing")   # CUDA events on the decoder's stream
         tm = dec.timing()
         score_ms.append(tm["score"]); beam_ms.append(tm["beam"])
+        busy_ms.append(dec.pipeline_info()["score_busy_ms"])
+    pinfo = dec.pipeline_info()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     t_wall1 = time.time()
@@ -427,7 +439,8 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
                dev_ms=dev_ms_max, wall_ms=wall_ms_max, e2e_ms=e2e_ms_max, h2d=h2d, d2h=d2h, launches=int(launches),
                score_ms=float(np.mean(score_ms)), beam_ms=float(np.mean(beam_ms)), clocks=clocks, phase=phase,
                n_ok=n_ok, n_res=len(res), failures=failures, tokens_per_frame=float(counts[:, 1].mean()), created_per_frame=float(counts[:, 0].mean()),
-               heap=hs, misspec=dec.misspeculations(), beam_width=int(ds.tree.beam_width), multipath=int(ds.tree.multipath))
+               heap=hs, misspec=dec.misspeculations(), beam_width=int(ds.tree.beam_width), multipath=int(ds.tree.multipath),
+               pipe_frames=pipe, pipe_slices=pinfo["slices"], score_busy_ms=float(np.mean(busy_ms)))
     if use_dnn:
         out["dnn_flops_per_frame"] = dnn_flops_per_frame
         out["dnn_layers"] = int(ds.dnn.n_layers); out["dnn_hidden"] = int(ds.dnn.layer_out[0])
@@ -444,6 +457,11 @@ def rooflines(r, world):
     B, T, S = r["B"], r["T"], r["S"]
     peak, peak_src = peaks()
     gmm_ms, bm_ms = r["score_ms"], r["beam_ms"]
+    piped = r.get("pipe_slices", 1) > 1
+    if piped:
+        # sliced batch: score_ms is only the scoring the beam had to wait for (slice 0); the scoring kernel's own time is
+        # the span its stream was busy, most of it beside the beam kernel
+        gmm_ms = r["score_busy_ms"]
     gmm_bytes = r["M_total"] * ALG_GMM_BYTES_PER_GAUSS + B * T * (r["D"] * 4 + 4 * S)
     beam_bytes = B * T * r["tokens_per_frame"] * ALG_BEAM_BYTES_PER_TOKEN
     beam_name = "beam_kernel_mp" if r["multipath"] else "beam_kernel"
@@ -470,6 +488,10 @@ def rooflines(r, world):
             "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_note": traffic_note,
             "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
             "kernel_ms": {score_name: gmm_ms, beam_name: bm_ms},
+            "pipeline": ({"slices": r["pipe_slices"], "frames_per_slice": r["pipe_frames"], "scoring_exposed_ms": r["score_ms"],
+                          "scoring_stream_busy_ms": r["score_busy_ms"], "beam_and_overlapped_scoring_ms": r["beam_ms"],
+                          "note": "scoring of slice c+1 runs on its own stream beside the token passing of slice c; "
+                                  "kernel_ms are spans, they overlap"} if piped else None),
             "beam_phase_cycles_per_frame": {n: round(float(c) / T, 1) for n, c in zip(
                 ("clear", "count_atoms", "expand", "creators", "order_sort", "materialise_outprob", "beam_cut", "heap_build"), r["phase"])},
             "beam_tokens_per_frame": r["tokens_per_frame"], "beam_created_per_frame": r["created_per_frame"],
@@ -566,7 +588,8 @@ def product_main(a):
         dist.init_process_group("nccl", device_id=device)
     ctx = dict(rank=rank, local=local, world=world, device=device, torch=torch, dist=dist)
 
-    r = measure_workload(ctx, a.workload, a.utts, a.frames, a.steps, a.warmup, mode=a.mode)
+    pf = PIPE_FRAMES_DEFAULT if a.pipe_frames < 0 else a.pipe_frames
+    r = measure_workload(ctx, a.workload, a.utts, a.frames, a.steps, a.warmup, mode=a.mode, pipe_frames=pf)
     B, T = r["B"], r["T"]
     extra = {}
     if world == 1 and not a.no_extra_legs:
@@ -604,7 +627,9 @@ def product_main(a):
                                                                 (", bf16x3 tensor-core arithmetic" if r["use_dnn"] else f", GMM arithmetic mode {a.mode}")),
                        "utts_per_gpu": B, "frames_per_utt": T, "resident_utts_per_gpu": r["resident"], "beam": r["beam_width"],
                        "l2": "per-step working set (score matrix %.1f GB) exceeds L2; %d distinct utterances per batch, two batches alternate" % (B * T * r["S"] * 4 / 1e9, B),
-                       "parallelism": f"utterance-sharded x{world}, no per-frame collective"},
+                       "parallelism": f"utterance-sharded x{world}, no per-frame collective",
+                       "pipeline": (f"batch cut into {r['pipe_slices']} time slices of {r['pipe_frames']} frames: GMM scoring of slice c+1 on a second "
+                                    f"stream beside the beam kernel of slice c" if r["pipe_slices"] > 1 else "off: one scoring launch, then one beam launch per batch")},
             "roofline": roof, "roofline_scoring": scoring,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"] // a.steps, "d2h_bytes_per_step": r["d2h"] // a.steps,
                     "ms_per_step": r["e2e_ms"] / a.steps},

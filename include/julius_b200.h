@@ -164,6 +164,42 @@ int jb200_decoder_phase_cycles(jb200_decoder *d, int64_t *cycles, int n_utts);
  * counts [T][2] = (tokens created, survivors) */
 int jb200_decoder_frame_counts(jb200_decoder *d, int u, int32_t *counts, int max_frames);
 
+/* ------------------------------------------------------------------------------------
+ * Batch pipeline.  With frames_per_slice > 0 a GMM batch is cut into time slices: the scoring of slice c+1 runs on its
+ * own CUDA stream beside the token passing of slice c (the FP32-bound scoring kernel and the latency-bound beam kernel
+ * share the SMs), provided the batch leaves room for a scoring thread block on every SM (n_utts <= 3/4 of
+ * jb200_decoder_resident_utts()).  Results are bit-identical to the unsliced batch.  0 (default, or JB200_PIPE_FRAMES
+ * in the environment) = one launch per batch.  jb200_decoder_last_timing() then reports [1] = the scoring the beam had
+ * to wait for (slice 0) and [2] = everything after; pipeline_info gives the slice count and how long the scoring stream
+ * was busy (overlapped).
+ * ---------------------------------------------------------------------------------- */
+int jb200_decoder_set_pipeline(jb200_decoder *d, int frames_per_slice);
+int jb200_decoder_pipeline_info(jb200_decoder *d, int32_t *n_slices, float *score_busy_ms);
+
+/* ------------------------------------------------------------------------------------
+ * Frame-synchronous operation ("streams").  The reference drives pass 1 one frame at a time,
+ *   get_back_trellis_init -> get_back_trellis_proceed(t) ... -> get_back_trellis_end -> finalize_1st_pass
+ *   (decode_proceed, libjulius/src/pass1.c:112-254; real-time input realtime-1stpass.c:681-, interim result
+ *   bt_current_max, beam.c:876-921 / :2983-2993),
+ * because with live input the utterance's length is not known in advance.  A stream is that call sequence: n_streams
+ * (<= max_utts) independent utterances advance together, each feed hands every stream its next n_new[s] >= 0 frames
+ * (feature vectors packed stream-major) and decodes them on the device; last[s] != 0 marks the end of stream s's
+ * utterance (its final frames, possibly none, come with the same call), after which jb200_stream_result() returns what
+ * jb200_decoder_results() returns for a batch.  Frame for frame the trellis is identical to the batch decode of the
+ * same vectors, whatever the feed sizes.  Per-stream capacity: max_frames / n_streams frames.
+ * ---------------------------------------------------------------------------------- */
+int jb200_stream_open(jb200_decoder *d, int n_streams);          /* all streams at the start of an utterance */
+int jb200_stream_restart(jb200_decoder *d, int stream);          /* one stream starts its next utterance */
+int jb200_stream_feed_host(jb200_decoder *d, const float *feats, const int32_t *n_new, const uint8_t *last, int want_interim);
+/* the same on a given state-score matrix ([sum n_new][n_states], host, log10) instead of feature vectors */
+int jb200_stream_feed_scores_host(jb200_decoder *d, const float *scores, const int32_t *n_new, const uint8_t *last, int want_interim);
+/* frames decoded so far; alive = 0 once the beam ran empty (get_back_trellis_proceed's FALSE, beam.c:3012-3015) */
+int jb200_stream_status(jb200_decoder *d, int stream, int32_t *frames_done, int32_t *alive, int32_t *ended);
+/* interim result of the last feed that asked for one (want_interim): the best word sequence ending at the last decoded
+ * frame, as bt_current_max publishes it in r->result.pass1 (word_num 0 = no word has ended there) */
+int jb200_stream_partial(jb200_decoder *d, int stream, int32_t *words, int max_words, int32_t *n_words, float *score, int32_t *frame);
+int jb200_stream_result(jb200_decoder *d, int stream, const jb200_utt_result **utt, const jb200_atom **atoms, const int32_t **words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,16 @@ def lib():
             L.jb200_decoder_heap_stats.argtypes = [vp, C.POINTER(C.c_int64)]
             L.jb200_decoder_select_stats.argtypes = [vp, C.POINTER(C.c_int64)]
             L.jb200_decoder_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
+            U8 = C.POINTER(C.c_uint8)
+            L.jb200_decoder_set_pipeline.argtypes = [vp, C.c_int]
+            L.jb200_decoder_pipeline_info.argtypes = [vp, D.I, D.F]
+            L.jb200_stream_open.argtypes = [vp, C.c_int]
+            L.jb200_stream_restart.argtypes = [vp, C.c_int]
+            L.jb200_stream_feed_host.argtypes = [vp, D.F, D.I, U8, C.c_int]
+            L.jb200_stream_feed_scores_host.argtypes = [vp, D.F, D.I, U8, C.c_int]
+            L.jb200_stream_status.argtypes = [vp, C.c_int, D.I, D.I, D.I]
+            L.jb200_stream_partial.argtypes = [vp, C.c_int, D.I, C.c_int, D.I, D.F, D.I]
+            L.jb200_stream_result.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         _lib = L
     return _lib
 
@@ -242,6 +252,61 @@ class Decoder:
 
     # the *_host entry points remember the batch size for results()
     _last_n = 0
+
+    # ---- batch pipeline: scoring of time slice c+1 beside the token passing of slice c
+    def set_pipeline(self, frames_per_slice: int):
+        _check(lib().jb200_decoder_set_pipeline(self._h, int(frames_per_slice)), "jb200_decoder_set_pipeline")
+
+    def pipeline_info(self) -> dict:
+        n, ms = C.c_int32(0), C.c_float(0)
+        _check(lib().jb200_decoder_pipeline_info(self._h, C.byref(n), C.byref(ms)), "jb200_decoder_pipeline_info")
+        return {"slices": int(n.value), "score_busy_ms": float(ms.value)}
+
+    # ---- frame-synchronous operation (jb200_stream_*): the call sequence get_back_trellis_init/_proceed/_end
+    def stream_open(self, n_streams: int = 1):
+        _check(lib().jb200_stream_open(self._h, n_streams), "jb200_stream_open")
+        self._st_n = n_streams
+
+    def stream_restart(self, stream: int):
+        _check(lib().jb200_stream_restart(self._h, stream), "jb200_stream_restart")
+
+    def stream_feed(self, chunks, last=None, interim: bool = False, scores: bool = False):
+        """chunks: one [n_new, dim] array (or None / empty) per stream; last: per-stream end-of-utterance flags."""
+        n = self._st_n
+        dim = None
+        for c in chunks:
+            if c is not None and len(c):
+                dim = c.shape[1]
+        n_new = np.array([0 if c is None else len(c) for c in chunks], np.int32)
+        parts = [np.asarray(c, np.float32) for c in chunks if c is not None and len(c)]
+        cat = np.ascontiguousarray(np.concatenate(parts, 0)) if parts else np.zeros((1, dim or 1), np.float32)
+        lastv = np.zeros(n, np.uint8) if last is None else np.asarray(last, np.uint8)
+        fn = lib().jb200_stream_feed_scores_host if scores else lib().jb200_stream_feed_host
+        _check(fn(self._h, _f(cat), n_new.ctypes.data_as(D.I), lastv.ctypes.data_as(C.POINTER(C.c_uint8)), 1 if interim else 0),
+               "jb200_stream_feed")
+
+    def stream_status(self, stream: int) -> dict:
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(lib().jb200_stream_status(self._h, stream, C.byref(a), C.byref(b), C.byref(c)), "jb200_stream_status")
+        return {"frames": int(a.value), "alive": bool(b.value), "ended": bool(c.value)}
+
+    def stream_partial(self, stream: int) -> dict:
+        w = np.zeros(160, np.int32)
+        n, sc, fr = C.c_int32(0), C.c_float(0), C.c_int32(0)
+        _check(lib().jb200_stream_partial(self._h, stream, w.ctypes.data_as(D.I), 160, C.byref(n), C.byref(sc), C.byref(fr)),
+               "jb200_stream_partial")
+        return {"words": w[:n.value].tolist(), "score": float(sc.value), "frame": int(fr.value)}
+
+    def stream_result(self, stream: int) -> dict:
+        pu, pa, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().jb200_stream_result(self._h, stream, C.byref(pu), C.byref(pa), C.byref(pw)), "jb200_stream_result")
+        u = np.ctypeslib.as_array(C.cast(pu.value, C.POINTER(C.c_uint8)), shape=(UTT_DT.itemsize,)).view(UTT_DT)[0]
+        na, nw = int(u["n_atoms"]), int(u["n_words"])
+        atoms = np.ctypeslib.as_array(C.cast(pa.value + int(u["atom_offset"]) * ATOM_DT.itemsize, C.POINTER(C.c_uint8)),
+                                      shape=(max(na, 0) * ATOM_DT.itemsize,)).view(ATOM_DT).copy() if na > 0 else np.zeros(0, ATOM_DT)
+        words = np.ctypeslib.as_array(C.cast(pw.value + int(u["word_offset"]) * 4, D.I), shape=(nw,)).copy().tolist() if nw > 0 else []
+        return dict(status=int(u["status"]), n_frames=int(u["n_frames"]), atoms=atoms, words=words,
+                    score=float(u["score"]), overflow=int(u["overflow"]))
 
     def handle_ptr(self):
         return self._h

@@ -42,7 +42,8 @@ namespace jb200 {
 int dnn_forward_device(jb200_dnn *h, const float *d_in, int T, float *d_rows, int row_stride, cudaStream_t st);
 int gmm_device(const jb200_gmm *h);
 int gmm_dim(const jb200_gmm *h);
-int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st);
+int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st,
+                      const int *seg_off, const int *seg_start, int n_seg);
 int gmm_cd_device(const jb200_gmm *h, const int **cd_off, const int **cd_states, int *method, int *nbest);
 
 #ifndef JB200_BEAM_THREADS
@@ -55,7 +56,7 @@ static constexpr unsigned SEQ_LOCAL = 1u << SEQ_LOCAL_BITS;
 static constexpr int CD_NMAX = 16;
 static constexpr int MAX_WORDS = 150;      // MAXSEQNUM, libsent/include/sent/speech.h:50
 
-struct __align__(16) NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, pad; int scid, out; };   // 32 B; (scid,out) is one aligned 8-byte word
+struct __align__(16) NodeRec { float self_a, next_a; int arc_off, arc_n; int stend, next; int scid, out; };   // 32 B; (scid,out) is one aligned 8-byte word; next = the node next_a leads to
 struct __align__(8) Tok { float score; int node; int tre; int cword; float lscore; int tre_wid; };              // 24 B
 struct __align__(16) Cand { float score; int node; float lscore; int src; };                                     // 16 B
 struct __align__(16) CandB { int tre; int cword; int tre_wid; int out; };                                        // 16 B: what the winner hands to the new token
@@ -73,6 +74,21 @@ struct SlotView {
     __stcg(reinterpret_cast<uint4 *>(s + node), make_uint4((unsigned)bestkey, (unsigned)(bestkey >> 32), (unsigned)firstseq, 0u));
   }
   __device__ __forceinline__ void reset(int node) const { set(node, 0x7fffffff, 0ull); }
+};
+
+// One launch of a beam kernel covers frames [t0, t1) of an utterance: the whole utterance (FIRST|FINAL), or one piece of
+// it -- the batch pipeline cuts utterances into chunks so that the scoring of chunk c+1 runs beside the token passing of
+// chunk c, and a stream (jb200_stream_*) advances as its input arrives, which is how the reference drives pass 1
+// (decode_proceed, one frame per call, libjulius/src/pass1.c:112-254).  Everything an utterance carries from frame to
+// frame lives in its global work area already; the few scalars the kernel keeps in shared memory are parked in UttState.
+static constexpr int CHUNK_FIRST = 1, CHUNK_FINAL = 2, CHUNK_SKIP = 4;   // SKIP: nothing to do for this utterance in this launch
+struct ChunkDesc { int t0, t1, flags, row_base; };   // score row of frame t: rows + (row_base + t) * row_stride
+struct UttState {
+  int ns, natoms, tnum_prev, slots_clean, overflow, stopped, cur, n_left;
+  float thr; int t_done;
+  // best partial sentence at the last frame done (bt_current_max, beam.c:876-921): filled when BeamParams.interim is set
+  int interim_frame, interim_nwords; float interim_score; int pad_;
+  long long prof[8];
 };
 
 struct BeamParams {
@@ -112,6 +128,9 @@ struct BeamParams {
   unsigned long long *heap_g; int sort_cap, qcap;      // qcap: 8-byte entries of the shared-memory area in front of offs (>= sort_cap)
   // grammar (DFA) mode, appended so that the offsets of everything above stay what the N-gram kernels were built with
   const uint8_t *cp_allowed; const int *init_node; const float *init_lscore; int n_init; float penalty1;
+  // chunked launches
+  const ChunkDesc *chunk; UttState *state; int interim; int *interim_words;   // [n_utts][MAX_WORDS]
+  int atoms_in_place;       // streams: the finalized atoms of utterance u go to atoms_out + atom_off[u] (no batch compaction)
 };
 
 // ---- small device helpers ----------------------------------------------------------------------
@@ -718,6 +737,28 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
   return 1;
 }
 
+
+// bt_current_max (beam.c:876-921): the best trellis word among those stored in the frame just done (raw atoms lo..hi-1,
+// end time frame-1), the most recently stored one on a tie (the reference walks its list newest first and keeps the
+// first maximum), traced back to the sentence start (trace_backptr, beam.c:253-301).  One thread.
+__device__ void interim_best(const BeamParams &p, const int u, const jb200_atom *araw, const int lo, const int hi, const int frame) {
+  UttState *st = p.state + u;
+  int best = -1; float mx = JB200_LOG_ZERO;
+  for (int a = hi - 1; a >= lo; a--) if (mx < araw[a].backscore) { mx = araw[a].backscore; best = a; }
+  st->interim_frame = frame - 1;
+  if (best < 0) { st->interim_nwords = 0; st->interim_score = JB200_LOG_ZERO; return; }
+  int *w = p.interim_words + (size_t)u * MAX_WORDS;
+  int n = 0, a = best;
+  w[n++] = araw[a].wid;
+  while (araw[a].begintime > 0) {
+    a = araw[a].last;
+    if (a < 0 || n >= MAX_WORDS) break;
+    w[n++] = araw[a].wid;
+  }
+  for (int i = 0; i < n / 2; i++) { const int x = w[i]; w[i] = w[n - 1 - i]; w[n - 1 - i] = x; }
+  st->interim_nwords = n; st->interim_score = mx;
+}
+
 // phase cycle accounting (thread 0 only; negligible cost)
 #define PROF_MARK(k) do { if (tid == 0) { long long _n = clock64(); s_prof[k] += _n - s_tprev; s_tprev = _n; } } while (0)
 
@@ -739,9 +780,12 @@ __device__ __forceinline__ void finalize_utt(const BeamParams &p, const int u, c
     newidx[a] = lo + rank;
   }
   if (tid == 0) {
-    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
-    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
-    else s_outbase = (long long)base;
+    if (p.atoms_in_place) s_outbase = p.atom_off[u];        // streams: each utterance keeps its own output region
+    else {
+      unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
+      if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
+      else s_outbase = (long long)base;
+    }
   }
   __syncthreads();
   const long long ob = s_outbase;
@@ -810,9 +854,12 @@ __device__ __forceinline__ void finalize_utt_grammar(const BeamParams &p, const 
     newidx[a] = lo + rank;
   }
   if (tid == 0) {
-    unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
-    if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
-    else s_outbase = (long long)base;
+    if (p.atoms_in_place) s_outbase = p.atom_off[u];        // streams: each utterance keeps its own output region
+    else {
+      unsigned long long base = atomicAdd(p.atom_counter, (unsigned long long)natoms);
+      if ((long long)(base + natoms) > p.atoms_out_cap) { s_overflow = 1; s_outbase = -1; }
+      else s_outbase = (long long)base;
+    }
   }
   __syncthreads();
   const long long ob = s_outbase;
@@ -916,7 +963,13 @@ __global__ void __launch_bounds__(BEAM_THREADS, JB200_BEAM_MINBLOCKS)
 beam_kernel_mp(const BeamParams p) {
   const int u = blockIdx.x;
   const int tid = threadIdx.x;
-  const int f_begin = p.frame_off[u], T = p.frame_off[u + 1] - f_begin;
+  // this launch covers frames [ck.t0, ck.t1) of the utterance (ChunkDesc); f_begin only addresses its work areas
+  const ChunkDesc ck = p.chunk[u];
+  if (ck.flags & CHUNK_SKIP) return;
+  const bool ck_first = (ck.flags & CHUNK_FIRST) != 0, ck_final = (ck.flags & CHUNK_FINAL) != 0;
+  UttState *const ust = p.state + u;
+  const int f_begin = p.frame_off[u];
+  const int T = ck.t1;                               // frames so far; the utterance's length when ck_final
   const int MAXT = p.maxt, MAXC = p.maxc, MAXW = p.maxw;
 
   // shared memory: [heap (MAXT+4 entries) | offs], or, when the heap lives in global memory, [sort area | offs]
@@ -956,12 +1009,15 @@ beam_kernel_mp(const BeamParams p) {
   jb200_utt_result *res = p.results + u;
   int *words = p.words + (size_t)u * MAX_WORDS;
 
-  if (tid == 0) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; s_found = -1;
-                  for (int k = 0; k < 8; k++) s_prof[k] = 0; s_tprev = clock64(); }
+  if (tid == 0) {
+    s_found = -1; s_tprev = clock64();
+    if (ck_first) { s_natoms = 0; s_overflow = 0; s_thr = JB200_LOG_ZERO; s_cur = 0; s_ns = 0; for (int k = 0; k < 8; k++) s_prof[k] = 0; }
+    else { s_natoms = ust->natoms; s_overflow = ust->overflow; s_thr = ust->thr; s_cur = ust->cur; s_ns = ust->ns; for (int k = 0; k < 8; k++) s_prof[k] = ust->prof[k]; }
+  }
   __syncthreads();
 
   // init_nodescore (beam.c:1631-1665): the word-begin node of <s> has no output (:1654-1656)
-  if (T > 0 && tid == 0) {
+  if (T > 0 && ck_first && tid == 0) {
     const int node = p.head_node;
     const NodeRec nr = p.nodes[node];
     Tok tk;
@@ -974,20 +1030,21 @@ beam_kernel_mp(const BeamParams p) {
   }
   __syncthreads();
 
-  int tnum_prev = (T > 0) ? 1 : 0;
-  int groups = T;
+  int tnum_prev = ck_first ? ((T > 0) ? 1 : 0) : ust->tnum_prev;
+  int stopped = ck_first ? -1 : ust->stopped;       // frame at which the beam ran empty (beam.c:3012-3015), -1 = alive
   int n_left = 0;             // tokens of the unfinished (final) frame whose node slots are still set
-  bool slots_clean = false;   // the previous frame's node slots were already reset under its second beam cut
+  bool slots_clean = ck_first ? false : (ust->slots_clean != 0);   // the previous frame's node slots were already reset under its second beam cut
 
   // frames 0..T-1 (pass1.c:239-245 calls proceed(0) right after init), then proceed(T, final) (beam.c:3066-3072)
-  for (int t = 0; t <= T && T > 0; t++) {
+  const int t_last = ck_final ? T : T - 1;
+  for (int t = ck.t0; t <= t_last && T > 0 && stopped < 0; t++) {
     const bool final = (t == T);
     const int cur = s_cur, nxt = cur ^ 1;
     Tok *tl = tok0 + (size_t)cur * MAXT, *tn = tok0 + (size_t)nxt * MAXT;
     int *ordl = ord0 + (size_t)cur * MAXT, *ordn = ord0 + (size_t)nxt * MAXT;
     const int ns = s_ns;
     const float thr = s_thr;
-    const float *row = p.rows + (size_t)(f_begin + (final ? 0 : t)) * p.row_stride;
+    const float *row = final ? p.rows : p.rows + (size_t)((long long)ck.row_base + t) * p.row_stride;   // the final half frame reads no scores
 
     // ---- P0: clear_tokens (normally done already under the previous frame's select #2)
     if (!slots_clean) {
@@ -1041,7 +1098,7 @@ beam_kernel_mp(const BeamParams p) {
       int next; float pa;
       const int has_self = (nr.self_a != JB200_LOG_ZERO), has_next = (nr.next_a != JB200_LOG_ZERO);
       if (has_self && k == 0) { next = tk.node; pa = nr.self_a; }
-      else if (has_next && k == has_self) { next = tk.node + 1; pa = nr.next_a; }
+      else if (has_next && k == has_self) { next = nr.next; pa = nr.next_a; }
       else { const int a = k - has_self - has_next; next = __ldg(p.arc_to + nr.arc_off + a); pa = __ldg(p.arc_a + nr.arc_off + a); }
       float tmpsum = tk.score + pa;
       float lsc = JB200_LOG_ZERO;
@@ -1423,8 +1480,23 @@ beam_kernel_mp(const BeamParams p) {
     }
     tnum_prev = ncre;
     __syncthreads();
-    if (ncre == 0) { groups = t; break; }      // beam.c:3012-3015
+    if (ncre == 0) { stopped = t; break; }      // beam.c:3012-3015
   }
+
+  if (!ck_final) {
+    // more frames to come: park the scalar state (everything else already lives in the utterance's global work area)
+    if (tid == 0) {
+      ust->natoms = s_natoms; ust->overflow = s_overflow; ust->thr = s_thr; ust->ns = s_ns; ust->cur = s_cur;
+      ust->tnum_prev = tnum_prev; ust->stopped = stopped; ust->slots_clean = slots_clean ? 1 : 0; ust->n_left = 0;
+      ust->t_done = T;
+      long long _n = clock64(); s_prof[7] += _n - s_tprev;
+      for (int k = 0; k < 8; k++) ust->prof[k] = s_prof[k];
+      // the word ends of frame T-1 were stored in half B of that frame (end time T-2)
+      if (p.interim) interim_best(p, u, araw, (T >= 2 && stopped < 0) ? group0[T - 2] : s_natoms, s_natoms, T - 1);
+    }
+    return;
+  }
+  const int groups = (stopped >= 0) ? stopped : T;
 
   {
     if (tid == 0 && T > 0) group0[groups] = s_natoms;
@@ -1490,6 +1562,22 @@ struct jb200_decoder {
   long long last_d2h = 0;
   int resident = 0;
   bool grammar = false;
+  // chunked launches: descriptors (a pinned staging copy and its device copy, one row of max_utts per chunk), parked state
+  static constexpr int MAX_CHUNKS = 64;
+  ChunkDesc *h_chunk = nullptr, *d_chunk = nullptr;
+  UttState *d_state = nullptr; int *d_interim_words = nullptr;
+  // batch pipeline: scoring of time slice c+1 on its own stream beside the token passing of slice c
+  cudaStream_t score_stream = nullptr;
+  cudaEvent_t ev_slice[MAX_CHUNKS]{}; cudaEvent_t ev_score_begin = nullptr, ev_score_end = nullptr;
+  int *h_seg = nullptr, *d_seg = nullptr;       // per slice: seg_off [max_utts+1] then seg_start [max_utts]
+  std::vector<int> slice_nseg, slice_frames;
+  int pipe_frames = 0;                          // frames per time slice; 0 = the pipeline is off
+  int n_chunks = 1; float last_score_busy_ms = 0.0f; bool last_piped = false;
+  // streams (jb200_stream_*)
+  bool stream_mode = false; int st_n = 0, st_cap = 0;
+  std::vector<int> st_t; std::vector<char> st_started, st_done;
+  long long *h_aoff = nullptr;                  // pinned copy of the per-utterance atom offsets
+  UttState *h_state = nullptr; int *h_interim_words = nullptr;
 };
 
 // from the shared-table arena when it has room, else an allocation of its own
@@ -1539,7 +1627,16 @@ extern "C" void jb200_decoder_destroy(jb200_decoder *d) {
   if (d->h_atoms) cudaFreeHost(d->h_atoms);
   if (d->h_words) cudaFreeHost(d->h_words);
   if (d->h_counter) cudaFreeHost(d->h_counter);
+  if (d->h_chunk) cudaFreeHost(d->h_chunk);
+  if (d->h_seg) cudaFreeHost(d->h_seg);
+  if (d->h_aoff) cudaFreeHost(d->h_aoff);
+  if (d->h_state) cudaFreeHost(d->h_state);
+  if (d->h_interim_words) cudaFreeHost(d->h_interim_words);
   for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : d->ev_slice) if (e) cudaEventDestroy(e);
+  if (d->ev_score_begin) cudaEventDestroy(d->ev_score_begin);
+  if (d->ev_score_end) cudaEventDestroy(d->ev_score_end);
+  if (d->score_stream) cudaStreamDestroy(d->score_stream);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -1588,28 +1685,60 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     if (getenv("JB200_NO_ARENA") == nullptr && cudaMalloc(&d->arena, est) == cudaSuccess) { d->arena_size = est; d->dev_allocs.push_back(d->arena); }
     else { d->arena = nullptr; cudaGetLastError(); }
   }
-  // node records
+  // Node numbering.  The host numbers the nodes word by word (a word's own nodes are consecutive), so the ~2400 nodes a
+  // frame touches are spread over the whole tree although 85 % of them sit in its first three levels (half of a frame's
+  // tokens are the roots that a word end fans out to): one 128-byte line of per-node arrival slots per token.  Node ids
+  // are not observable outside the decoder, so the tree is renumbered breadth-first from the roots (roots in their list
+  // order, then level by level): the slots and node records a frame touches become a few dense ranges -- 3.4x fewer
+  // slot lines, 2.1x fewer node-record lines per frame on the 20k-word tree (tools/node_locality.py).  `next_a` no longer
+  // leads to id+1, so the record carries the successor explicitly.  JB200_NO_RENUMBER=1 keeps the host's numbering.
+  std::vector<int> perm(n), inv(n);
+  {
+    std::vector<int> order; order.reserve(n);
+    std::vector<char> seen(n, 0);
+    auto push = [&](int x) { if (x >= 0 && x < n && !seen[x]) { seen[x] = 1; order.push_back(x); } };
+    if (getenv("JB200_NO_RENUMBER") == nullptr || atoi(getenv("JB200_NO_RENUMBER")) == 0) {
+      for (int i = 0; i < t->n_iso; i++) push(t->iso_node[i]);
+      for (int i = 0; i < t->n_shared; i++) push(t->shared_node[i]);
+      if (grammar) for (int i = 0; i < t->n_init; i++) push(t->init_node[i]);
+      for (size_t q = 0; q < order.size(); q++) {
+        const int x = order[q];
+        if (t->next_a[x] != JB200_LOG_ZERO) push(x + 1);
+        for (int k = t->arc_off[x]; k < t->arc_off[x + 1]; k++) push(t->arc_to[k]);
+      }
+    }
+    for (int x = 0; x < n; x++) push(x);                       // whatever the roots do not reach keeps its relative order
+    for (int i = 0; i < n; i++) { perm[order[i]] = i; inv[i] = order[i]; }
+  }
+  auto remap = [&](const int *src, size_t cnt) { std::vector<int> v(cnt); for (size_t i = 0; i < cnt; i++) v[i] = perm[src[i]]; return v; };
+  // node records and the arc lists, in the new order
   std::vector<NodeRec> nodes(n);
-  for (int i = 0; i < n; i++) {
-    NodeRec &r = nodes[i];
-    r.self_a = t->self_a[i]; r.next_a = t->next_a[i];
-    r.arc_off = t->arc_off[i]; r.arc_n = t->arc_off[i + 1] - t->arc_off[i];
-    r.stend = t->stend[i]; r.scid = t->scid[i];
-    const int style = t->outstyle[i];
-    if (style > 3 && !(style == 255 && t->multipath)) { set_error("non-emitting node in a non-multipath tree"); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
-    r.out = (style == 255) ? (int)0xF0000000u : (int)(((unsigned)style << 28) | (unsigned)(t->out_ref[i] & 0x0fffffff));
-    r.pad = 0;
+  std::vector<int> arc_to_n((size_t)std::max(t->n_arcs, 1)); std::vector<float> arc_a_n((size_t)std::max(t->n_arcs, 1));
+  {
+    int ao = 0;
+    for (int i = 0; i < n; i++) {
+      const int o = inv[i];
+      NodeRec &r = nodes[i];
+      r.self_a = t->self_a[o]; r.next_a = t->next_a[o];
+      r.arc_off = ao; r.arc_n = t->arc_off[o + 1] - t->arc_off[o];
+      for (int k = t->arc_off[o]; k < t->arc_off[o + 1]; k++) { arc_to_n[ao] = perm[t->arc_to[k]]; arc_a_n[ao] = t->arc_a[k]; ao++; }
+      r.stend = t->stend[o]; r.scid = t->scid[o];
+      const int style = t->outstyle[o];
+      if (style > 3 && !(style == 255 && t->multipath)) { set_error("non-emitting node in a non-multipath tree"); jb200_decoder_destroy(d); return JB200_ERR_UNSUPPORTED; }
+      r.out = (style == 255) ? (int)0xF0000000u : (int)(((unsigned)style << 28) | (unsigned)(t->out_ref[o] & 0x0fffffff));
+      r.next = (r.next_a != JB200_LOG_ZERO && o + 1 < n) ? perm[o + 1] : i;
+    }
   }
   TRY(dev_upload(d, nodes.data(), nodes.size(), &P.nodes));
-  TRY(dev_upload(d, t->arc_to, (size_t)t->n_arcs, &P.arc_to));
-  TRY(dev_upload(d, t->arc_a, (size_t)t->n_arcs, &P.arc_a));
+  TRY(dev_upload(d, arc_to_n.data(), (size_t)t->n_arcs, &P.arc_to));
+  TRY(dev_upload(d, arc_a_n.data(), (size_t)t->n_arcs, &P.arc_a));
   TRY(dev_upload(d, t->rset_ctx, (size_t)t->n_rset * (t->n_ctx + 1), &P.rset_ctx));
   TRY(dev_upload(d, t->word_ctx, (size_t)t->n_words, &P.word_ctx));
   P.n_ctx = t->n_ctx;
-  TRY(dev_upload(d, t->iso_node, (size_t)t->n_iso, &P.iso_node));
+  { const std::vector<int> v = remap(t->iso_node, (size_t)t->n_iso); TRY(dev_upload(d, v.data(), v.size(), &P.iso_node)); }
   TRY(dev_upload(d, t->iso_id, (size_t)t->n_iso, &P.iso_id));
   P.n_iso = t->n_iso;
-  TRY(dev_upload(d, t->shared_node, (size_t)t->n_shared, &P.shared_node));
+  { const std::vector<int> v = remap(t->shared_node, (size_t)t->n_shared); TRY(dev_upload(d, v.data(), v.size(), &P.shared_node)); }
   {
     std::vector<float> sf(std::max(t->n_shared, 1));
     for (int i = 0; i < t->n_shared; i++) {
@@ -1624,7 +1753,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.cp_allowed = nullptr; P.init_node = nullptr; P.init_lscore = nullptr; P.n_init = 0; P.penalty1 = 0.0f;
   if (grammar) {
     TRY(dev_upload(d, t->cp_allowed, (size_t)t->n_words * t->n_iso, &P.cp_allowed));
-    TRY(dev_upload(d, t->init_node, (size_t)t->n_init, &P.init_node));
+    { const std::vector<int> v = remap(t->init_node, (size_t)t->n_init); TRY(dev_upload(d, v.data(), v.size(), &P.init_node)); }
     TRY(dev_upload(d, t->init_lscore, (size_t)t->n_init, &P.init_lscore));
     P.n_init = t->n_init; P.penalty1 = t->penalty1;
   }
@@ -1634,9 +1763,9 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     std::vector<int> ia_node, ia_iso, sa_node, sa_sh; std::vector<float> ia_a, sa_a;
     if (t->multipath) {
       auto expand = [&](int root, int idx, std::vector<int> &vn, std::vector<int> &vi, std::vector<float> &va) {
-        if (t->self_a[root] != JB200_LOG_ZERO) { vn.push_back(root); vi.push_back(idx); va.push_back(t->self_a[root]); }
-        if (t->next_a[root] != JB200_LOG_ZERO) { vn.push_back(root + 1); vi.push_back(idx); va.push_back(t->next_a[root]); }
-        for (int k = t->arc_off[root]; k < t->arc_off[root + 1]; k++) { vn.push_back(t->arc_to[k]); vi.push_back(idx); va.push_back(t->arc_a[k]); }
+        if (t->self_a[root] != JB200_LOG_ZERO) { vn.push_back(perm[root]); vi.push_back(idx); va.push_back(t->self_a[root]); }
+        if (t->next_a[root] != JB200_LOG_ZERO) { vn.push_back(perm[root + 1]); vi.push_back(idx); va.push_back(t->next_a[root]); }
+        for (int k = t->arc_off[root]; k < t->arc_off[root + 1]; k++) { vn.push_back(perm[t->arc_to[k]]); vi.push_back(idx); va.push_back(t->arc_a[k]); }
       };
       const int head_begin = t->wordbegin[t->head_silwid];
       for (int i = 0; i < t->n_iso; i++) if (t->iso_node[i] != head_begin) expand(t->iso_node[i], i, ia_node, ia_iso, ia_a);
@@ -1669,7 +1798,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   P.lm_mode = t->lm_mode; P.lm_unk_id = t->lm_unk_id; P.lm_unk_num_log = t->lm_unk_num_log;
   P.lm_weight = t->lm_weight; P.lm_penalty = t->lm_penalty; P.lm_penalty_trans = t->lm_penalty_trans;
   P.prune_width = t->score_pruning_width;
-  P.head_node = grammar ? 0 : t->wordbegin[t->head_silwid]; P.tail_silwid = t->tail_silwid; P.beam = t->beam_width; P.n_nodes = n;
+  P.head_node = grammar ? 0 : perm[t->wordbegin[t->head_silwid]]; P.tail_silwid = t->tail_silwid; P.beam = t->beam_width; P.n_nodes = n;
   // cd sets come from the AM handle's descriptor: re-upload from the gmm handle is not exposed, so the
   // decoder asks the scorer for its device copies
   {
@@ -1749,6 +1878,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
       TRYC(cudaMemsetAsync(P.lmc, 0xff, sizeof(unsigned long long) << bits, d->stream));
     }
   }
+  P.chunk = nullptr; P.state = nullptr; P.interim = 0; P.interim_words = nullptr; P.atoms_in_place = 0;
   P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   P.no_closed = getenv("JB200_NO_CLOSED_FORM") ? atoi(getenv("JB200_NO_CLOSED_FORM")) : 0;   // 1: always replay the extraction loop
@@ -1777,6 +1907,27 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   TRYC(cudaMallocHost(&d->h_atoms, sizeof(jb200_atom) * (size_t)d->atoms_cap));
   TRYC(cudaMallocHost(&d->h_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
   TRYC(cudaMallocHost(&d->h_counter, sizeof(unsigned long long)));
+  TRY(dev_alloc(d, (size_t)jb200_decoder::MAX_CHUNKS * max_utts, &d->d_chunk));
+  TRYC(cudaMallocHost(&d->h_chunk, sizeof(ChunkDesc) * (size_t)jb200_decoder::MAX_CHUNKS * max_utts));
+  TRY(dev_alloc(d, (size_t)max_utts, &d->d_state));
+  TRYC(cudaMemset(d->d_state, 0, sizeof(UttState) * (size_t)max_utts));
+  TRY(dev_alloc(d, (size_t)max_utts * MAX_WORDS, &d->d_interim_words));
+  TRY(dev_alloc(d, (size_t)jb200_decoder::MAX_CHUNKS * (2 * max_utts + 1), &d->d_seg));
+  TRYC(cudaMallocHost(&d->h_seg, sizeof(int) * (size_t)jb200_decoder::MAX_CHUNKS * (2 * max_utts + 1)));
+  TRYC(cudaMallocHost(&d->h_aoff, sizeof(long long) * (size_t)(max_utts + 1)));
+  TRYC(cudaMallocHost(&d->h_state, sizeof(UttState) * (size_t)max_utts));
+  TRYC(cudaMallocHost(&d->h_interim_words, sizeof(int) * (size_t)max_utts * MAX_WORDS));
+  {
+    // the scoring stream of the batch pipeline gets the higher priority: its thread blocks take the room the token-passing
+    // kernel leaves on every SM as soon as it is free
+    int lo = 0, hi = 0;
+    TRYC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TRYC(cudaStreamCreateWithPriority(&d->score_stream, cudaStreamNonBlocking, hi));
+    for (auto &e : d->ev_slice) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRYC(cudaEventCreate(&d->ev_score_begin)); TRYC(cudaEventCreate(&d->ev_score_end));
+    d->pipe_frames = 0;
+    if (const char *e = getenv("JB200_PIPE_FRAMES")) d->pipe_frames = std::max(0, atoi(e));
+  }
   d->smem_bytes = (heap_global ? (size_t)P.qcap * 8 + (size_t)(t->beam_width + 2) * 8 : (size_t)(maxt + 4) * 8) + offs_bytes;
   d->grammar = grammar;
   const void *kern = grammar ? (const void *)beam_kernel_grammar : P.multipath ? (const void *)beam_kernel_mp : (const void *)beam_kernel;
@@ -1814,38 +1965,116 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
   return JB200_OK;
 }
 
-static int prepare_batch(jb200_decoder *d, const int32_t *frame_off, int n_utts) {
+// Cut a batch into time slices.  One slice (the whole utterance per launch) unless the pipeline is on: then slice c holds
+// frames [c*F, (c+1)*F) of every utterance, scored by its own launch on the scoring stream (a gather over the segment
+// list) while the beam kernel works on slice c-1.  Fills the staging copies of the chunk descriptors and segment lists.
+static int plan_slices(jb200_decoder *d, const int32_t *frame_off, int n_utts, bool allow_pipe) {
+  int maxT = 0;
+  for (int u = 0; u < n_utts; u++) maxT = std::max(maxT, frame_off[u + 1] - frame_off[u]);
+  int F = (allow_pipe && !d->dnn && d->pipe_frames > 0) ? d->pipe_frames : 0;
+  int nch = 1;
+  if (F > 0) {
+    nch = (maxT + F - 1) / F;
+    if (nch > jb200_decoder::MAX_CHUNKS) { F = (maxT + jb200_decoder::MAX_CHUNKS - 1) / jb200_decoder::MAX_CHUNKS; nch = (maxT + F - 1) / F; }
+    if (nch < 2) { nch = 1; F = 0; }
+  }
+  d->n_chunks = nch; d->last_piped = (F > 0);
+  d->slice_nseg.assign(nch, 0); d->slice_frames.assign(nch, 0);
+  const int mu = d->max_utts, segw = 2 * mu + 1;
+  for (int c = 0; c < nch; c++) {
+    ChunkDesc *cd = d->h_chunk + (size_t)c * mu;
+    int *so = d->h_seg + (size_t)c * segw, *ss = so + mu + 1;     // seg_off [mu+1], seg_start [mu]
+    int nseg = 0, lf = 0;
+    for (int u = 0; u < n_utts; u++) {
+      const int T = frame_off[u + 1] - frame_off[u];
+      ChunkDesc k;
+      k.row_base = frame_off[u];
+      if (F == 0) { k.t0 = 0; k.t1 = T; k.flags = CHUNK_FIRST | CHUNK_FINAL; }
+      else {
+        k.t0 = std::min(c * F, T); k.t1 = std::min((c + 1) * F, T);
+        const bool past = (c > 0) && (c * F >= T);             // the utterance ended in an earlier slice
+        const bool last = ((c + 1) * F >= T);
+        k.flags = past ? CHUNK_SKIP : ((c == 0 ? CHUNK_FIRST : 0) | (last ? CHUNK_FINAL : 0));
+        if (!past && k.t1 > k.t0) { so[nseg] = lf; ss[nseg] = frame_off[u] + k.t0; nseg++; lf += k.t1 - k.t0; }
+      }
+      cd[u] = k;
+    }
+    so[nseg] = lf;
+    d->slice_nseg[c] = nseg; d->slice_frames[c] = lf;
+  }
+  return JB200_OK;
+}
+
+static int prepare_batch(jb200_decoder *d, const int32_t *frame_off, int n_utts, bool allow_pipe = true) {
   if (!d || !frame_off || n_utts < 1) { set_error("decode: bad argument"); return JB200_ERR_ARG; }
   if (n_utts > d->max_utts) { set_error("batch of %d utterances exceeds decoder capacity %d", n_utts, d->max_utts); return JB200_ERR_CAPACITY; }
   const int total = frame_off[n_utts] - frame_off[0];
   if (frame_off[0] != 0) { set_error("frame_off[0] must be 0"); return JB200_ERR_ARG; }
   if (total > d->max_frames) { set_error("batch of %d frames exceeds decoder capacity %d", total, d->max_frames); return JB200_ERR_CAPACITY; }
-  std::vector<long long> aoff(n_utts + 1);
-  aoff[0] = 0;
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaStreamSynchronize(d->stream));   // the staging buffers below may still feed the previous batch's copies
+  d->h_aoff[0] = 0;
   for (int u = 0; u < n_utts; u++) {
     const int T = frame_off[u + 1] - frame_off[u];
     if (T < 0 || T > 32767) { set_error("utterance %d has %d frames (trellis times are 16-bit in the reference)", u, T); return JB200_ERR_ARG; }
-    aoff[u + 1] = aoff[u] + (long long)T * d->atoms_per_frame + 64;
+    d->h_aoff[u + 1] = d->h_aoff[u] + (long long)T * d->atoms_per_frame + 64;
   }
-  JB_CUDA(cudaSetDevice(d->device));
+  d->stream_mode = false;
   d->h_frame_off.assign(frame_off, frame_off + n_utts + 1);
-  JB_CUDA(cudaMemcpyAsync(d->d_frame_off, frame_off, sizeof(int) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
-  JB_CUDA(cudaMemcpyAsync(d->d_atom_off, aoff.data(), sizeof(long long) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
+  int rc = plan_slices(d, frame_off, n_utts, allow_pipe); if (rc) return rc;
+  const int mu = d->max_utts;
+  JB_CUDA(cudaMemcpyAsync(d->d_frame_off, d->h_frame_off.data(), sizeof(int) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->d_atom_off, d->h_aoff, sizeof(long long) * (n_utts + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->d_chunk, d->h_chunk, sizeof(ChunkDesc) * (size_t)d->n_chunks * mu, cudaMemcpyHostToDevice, d->stream));
+  if (d->last_piped)
+    JB_CUDA(cudaMemcpyAsync(d->d_seg, d->h_seg, sizeof(int) * (size_t)d->n_chunks * (2 * mu + 1), cudaMemcpyHostToDevice, d->stream));
   JB_CUDA(cudaMemsetAsync(d->d_atom_counter, 0, sizeof(unsigned long long), d->stream));
-  JB_CUDA(cudaStreamSynchronize(d->stream));   // aoff is a local
+  JB_CUDA(cudaStreamSynchronize(d->stream));   // h_frame_off is a std::vector (pageable)
   d->last_n = n_utts; d->last_total_frames = total; d->fetched = false;
   return JB200_OK;
 }
 
-static int launch_beam(jb200_decoder *d, int n_utts) {
+static int launch_beam(jb200_decoder *d, int n_utts, int chunk_index = 0, int interim = 0) {
   BeamParams P = d->P;
   P.rows = d->d_rows; P.row_stride = d->row_stride; P.frame_off = d->d_frame_off;
   P.atom_off = d->d_atom_off; P.atoms_out = d->d_atoms_out; P.atom_counter = d->d_atom_counter;
   P.atoms_out_cap = d->atoms_cap; P.results = d->d_results; P.words = d->d_words; P.prof = d->d_prof;
+  P.chunk = d->d_chunk + (size_t)chunk_index * d->max_utts; P.state = d->d_state;
+  P.interim = interim; P.interim_words = d->d_interim_words; P.atoms_in_place = d->stream_mode ? 1 : 0;
   if (d->grammar) beam_kernel_grammar<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   else if (P.multipath) beam_kernel_mp<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   else beam_kernel<<<n_utts, BEAM_THREADS, d->smem_bytes, d->stream>>>(P);
   JB_LAUNCH_CHECK();
+  return JB200_OK;
+}
+
+// scoring + token passing of a prepared batch whose features are at d_feats; ev[1] has been recorded on the main stream
+static int run_batch(jb200_decoder *d, const float *d_feats, int n_utts) {
+  int rc;
+  if (!d->last_piped) {
+    rc = d->dnn ? dnn_forward_device(d->dnn, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream)
+                : gmm_launch_states(d->am, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream, nullptr, nullptr, 0);
+    if (rc) return rc;
+    JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    return launch_beam(d, n_utts, 0);
+  }
+  // pipeline: every slice's scoring is queued on the scoring stream at once (it only depends on the features), the beam
+  // kernel of slice c waits for the scores of slice c alone
+  const int mu = d->max_utts, segw = 2 * mu + 1;
+  JB_CUDA(cudaStreamWaitEvent(d->score_stream, d->ev[1], 0));
+  JB_CUDA(cudaEventRecord(d->ev_score_begin, d->score_stream));
+  for (int c = 0; c < d->n_chunks; c++) {
+    const int *ds = d->d_seg + (size_t)c * segw;
+    rc = gmm_launch_states(d->am, d_feats, d->slice_frames[c], d->d_rows, d->row_stride, d->score_stream, ds, ds + mu + 1, d->slice_nseg[c]);
+    if (rc) return rc;
+    JB_CUDA(cudaEventRecord(d->ev_slice[c], d->score_stream));
+  }
+  JB_CUDA(cudaEventRecord(d->ev_score_end, d->score_stream));
+  for (int c = 0; c < d->n_chunks; c++) {
+    JB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_slice[c], 0));
+    if (c == 0) JB_CUDA(cudaEventRecord(d->ev[2], d->stream));       // "scoring" = what the beam had to wait for
+    rc = launch_beam(d, n_utts, c); if (rc) return rc;
+  }
   return JB200_OK;
 }
 
@@ -1868,6 +2097,7 @@ extern "C" int jb200_decoder_fetch(jb200_decoder *d) {
   cudaEventElapsedTime(&d->last_ms[1], d->ev[1], d->ev[2]);
   cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
   cudaEventElapsedTime(&d->last_ms[3], d->ev[3], d->ev[4]);
+  if (d->last_piped) cudaEventElapsedTime(&d->last_score_busy_ms, d->ev_score_begin, d->ev_score_end);
   d->last_d2h = (long long)sizeof(unsigned long long) + (long long)sizeof(jb200_utt_result) * d->last_n +
                 (long long)sizeof(int) * d->last_n * MAX_WORDS + (long long)sizeof(jb200_atom) * na;
   d->fetched = true;
@@ -1881,6 +2111,7 @@ extern "C" int jb200_decoder_sync_timing(jb200_decoder *d) {
   cudaEventElapsedTime(&d->last_ms[0], d->ev[0], d->ev[1]);
   cudaEventElapsedTime(&d->last_ms[1], d->ev[1], d->ev[2]);
   cudaEventElapsedTime(&d->last_ms[2], d->ev[2], d->ev[3]);
+  if (d->last_piped) cudaEventElapsedTime(&d->last_score_busy_ms, d->ev_score_begin, d->ev_score_end);
   d->last_ms[3] = 0.0f;
   return JB200_OK;
 }
@@ -1943,11 +2174,7 @@ extern "C" int jb200_decode_batch_device(jb200_decoder *d, const float *d_feats,
   int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
   JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
-  rc = d->dnn ? dnn_forward_device(d->dnn, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream)
-              : gmm_launch_states(d->am, d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream);
-  if (rc) return rc;
-  JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
-  rc = launch_beam(d, n_utts); if (rc) return rc;
+  rc = run_batch(d, d_feats, n_utts); if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[3], d->stream));
   return JB200_OK;
 }
@@ -1958,24 +2185,190 @@ extern "C" int jb200_decode_batch_host(jb200_decoder *d, const float *feats, con
   JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
   JB_CUDA(cudaMemcpyAsync(d->d_feats, feats, sizeof(float) * (size_t)d->last_total_frames * d->dim, cudaMemcpyHostToDevice, d->stream));
   JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
-  rc = d->dnn ? dnn_forward_device(d->dnn, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream)
-              : gmm_launch_states(d->am, d->d_feats, d->last_total_frames, d->d_rows, d->row_stride, d->stream);
-  if (rc) return rc;
-  JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
-  rc = launch_beam(d, n_utts); if (rc) return rc;
+  rc = run_batch(d, d->d_feats, n_utts); if (rc) return rc;
   return jb200_decoder_fetch(d);
 }
 
 extern "C" int jb200_decode_batch_scores_host(jb200_decoder *d, const float *scores, const int32_t *frame_off, int n_utts) {
   if (!scores) { set_error("null scores"); return JB200_ERR_ARG; }
-  int rc = prepare_batch(d, frame_off, n_utts); if (rc) return rc;
+  int rc = prepare_batch(d, frame_off, n_utts, false); if (rc) return rc;
   JB_CUDA(cudaEventRecord(d->ev[0], d->stream));
   JB_CUDA(cudaMemcpy2DAsync(d->d_rows, sizeof(float) * d->row_stride, scores, sizeof(float) * d->S, sizeof(float) * d->S,
                             d->last_total_frames, cudaMemcpyHostToDevice, d->stream));
   JB_CUDA(cudaEventRecord(d->ev[1], d->stream));
   JB_CUDA(cudaEventRecord(d->ev[2], d->stream));
-  rc = launch_beam(d, n_utts); if (rc) return rc;
+  rc = launch_beam(d, n_utts, 0); if (rc) return rc;
   return jb200_decoder_fetch(d);
+}
+
+// ---- frame-synchronous operation (streams) -----------------------------------------------------------------------
+extern "C" int jb200_stream_open(jb200_decoder *d, int n_streams) {
+  if (!d || n_streams < 1) { set_error("jb200_stream_open: bad argument"); return JB200_ERR_ARG; }
+  if (n_streams > d->max_utts) { set_error("%d streams exceed decoder capacity %d", n_streams, d->max_utts); return JB200_ERR_CAPACITY; }
+  JB_CUDA(cudaSetDevice(d->device));
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  // a stream that was abandoned before its last frame has left node slots behind: wipe those work areas
+  if (d->stream_mode) {
+    for (int u = 0; u < d->st_n; u++) if (d->st_started[u] && !d->st_done[u]) {
+      const size_t tot = (size_t)d->P.n_nodes;
+      fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(d->P.slots + (size_t)u * d->P.n_nodes, tot);
+      JB_LAUNCH_CHECK();
+    }
+  }
+  const int cap = std::min(d->max_frames / n_streams, 32767);
+  if (cap < 1) { set_error("decoder capacity of %d frames is too small for %d streams", d->max_frames, n_streams); return JB200_ERR_CAPACITY; }
+  d->stream_mode = true; d->st_n = n_streams; d->st_cap = cap;
+  d->st_t.assign(n_streams, 0); d->st_started.assign(n_streams, 0); d->st_done.assign(n_streams, 0);
+  d->h_frame_off.assign(n_streams + 1, 0);
+  d->h_aoff[0] = 0;
+  for (int u = 0; u < n_streams; u++) {
+    d->h_frame_off[u + 1] = d->h_frame_off[u] + cap;
+    d->h_aoff[u + 1] = d->h_aoff[u] + (long long)cap * d->atoms_per_frame + 64;
+  }
+  JB_CUDA(cudaMemcpyAsync(d->d_frame_off, d->h_frame_off.data(), sizeof(int) * (n_streams + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaMemcpyAsync(d->d_atom_off, d->h_aoff, sizeof(long long) * (n_streams + 1), cudaMemcpyHostToDevice, d->stream));
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  d->last_n = n_streams; d->n_chunks = 1; d->last_piped = false; d->fetched = true;
+  return JB200_OK;
+}
+
+// device part shared by the feature / score variants: rows of the new frames are in d_rows, packed stream-major
+static int stream_advance(jb200_decoder *d, const int32_t *n_new, const uint8_t *last, int want_interim) {
+  int pack = 0, any = 0;
+  for (int u = 0; u < d->st_n; u++) {
+    ChunkDesc k; k.t0 = d->st_t[u]; k.t1 = k.t0 + n_new[u]; k.row_base = pack - k.t0; k.flags = 0;
+    const bool fin = last && last[u];
+    if (d->st_done[u] || (n_new[u] == 0 && !fin)) k.flags = CHUNK_SKIP;
+    else {
+      if (!d->st_started[u]) k.flags |= CHUNK_FIRST;
+      if (fin) k.flags |= CHUNK_FINAL;
+      any = 1;
+    }
+    d->h_chunk[u] = k;
+    pack += n_new[u];
+  }
+  if (!any) return JB200_OK;
+  JB_CUDA(cudaMemcpyAsync(d->d_chunk, d->h_chunk, sizeof(ChunkDesc) * (size_t)d->st_n, cudaMemcpyHostToDevice, d->stream));
+  int rc = launch_beam(d, d->st_n, 0, want_interim); if (rc) return rc;
+  // results of the streams that ended; interim state of the others
+  bool fin_any = false;
+  for (int u = 0; u < d->st_n; u++) if (d->h_chunk[u].flags & CHUNK_FINAL) fin_any = true;
+  if (fin_any) {
+    JB_CUDA(cudaMemcpyAsync(d->h_results, d->d_results, sizeof(jb200_utt_result) * d->st_n, cudaMemcpyDeviceToHost, d->stream));
+    JB_CUDA(cudaMemcpyAsync(d->h_words, d->d_words, sizeof(int) * (size_t)d->st_n * MAX_WORDS, cudaMemcpyDeviceToHost, d->stream));
+  }
+  JB_CUDA(cudaMemcpyAsync(d->h_state, d->d_state, sizeof(UttState) * (size_t)d->st_n, cudaMemcpyDeviceToHost, d->stream));
+  if (want_interim)
+    JB_CUDA(cudaMemcpyAsync(d->h_interim_words, d->d_interim_words, sizeof(int) * (size_t)d->st_n * MAX_WORDS, cudaMemcpyDeviceToHost, d->stream));
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  d->last_d2h = 0;
+  for (int u = 0; u < d->st_n; u++) {
+    const int fl = d->h_chunk[u].flags;
+    if (fl & CHUNK_SKIP) continue;
+    d->st_started[u] = 1; d->st_t[u] = d->h_chunk[u].t1;
+    if (fl & CHUNK_FINAL) {
+      d->st_done[u] = 1;
+      const int na = d->h_results[u].n_atoms;
+      if (na > 0) JB_CUDA(cudaMemcpyAsync(d->h_atoms + d->h_aoff[u], d->d_atoms_out + d->h_aoff[u], sizeof(jb200_atom) * (size_t)na, cudaMemcpyDeviceToHost, d->stream));
+      d->last_d2h += (long long)sizeof(jb200_atom) * na + (long long)sizeof(jb200_utt_result) + (long long)sizeof(int) * MAX_WORDS;
+    }
+  }
+  JB_CUDA(cudaStreamSynchronize(d->stream));
+  return JB200_OK;
+}
+
+static int stream_check(jb200_decoder *d, const int32_t *n_new, int *total) {
+  if (!d || !n_new) { set_error("jb200_stream_feed: bad argument"); return JB200_ERR_ARG; }
+  if (!d->stream_mode) { set_error("jb200_stream_feed: call jb200_stream_open first"); return JB200_ERR_ARG; }
+  int tot = 0;
+  for (int u = 0; u < d->st_n; u++) {
+    if (n_new[u] < 0) { set_error("stream %d: negative frame count", u); return JB200_ERR_ARG; }
+    if (d->st_done[u] && n_new[u] > 0) { set_error("stream %d has ended; restart it before feeding more frames", u); return JB200_ERR_ARG; }
+    if (d->st_t[u] + n_new[u] > d->st_cap) { set_error("stream %d: %d frames exceed the per-stream capacity %d", u, d->st_t[u] + n_new[u], d->st_cap); return JB200_ERR_CAPACITY; }
+    tot += n_new[u];
+  }
+  if (tot > d->max_frames) { set_error("%d new frames exceed decoder capacity %d", tot, d->max_frames); return JB200_ERR_CAPACITY; }
+  *total = tot;
+  return JB200_OK;
+}
+
+extern "C" int jb200_stream_feed_host(jb200_decoder *d, const float *feats, const int32_t *n_new, const uint8_t *last, int want_interim) {
+  int tot = 0;
+  int rc = stream_check(d, n_new, &tot); if (rc) return rc;
+  if (tot > 0 && !feats) { set_error("null feats"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  if (tot > 0) {
+    JB_CUDA(cudaMemcpyAsync(d->d_feats, feats, sizeof(float) * (size_t)tot * d->dim, cudaMemcpyHostToDevice, d->stream));
+    rc = d->dnn ? dnn_forward_device(d->dnn, d->d_feats, tot, d->d_rows, d->row_stride, d->stream)
+                : gmm_launch_states(d->am, d->d_feats, tot, d->d_rows, d->row_stride, d->stream, nullptr, nullptr, 0);
+    if (rc) return rc;
+  }
+  return stream_advance(d, n_new, last, want_interim);
+}
+
+extern "C" int jb200_stream_feed_scores_host(jb200_decoder *d, const float *scores, const int32_t *n_new, const uint8_t *last, int want_interim) {
+  int tot = 0;
+  int rc = stream_check(d, n_new, &tot); if (rc) return rc;
+  if (tot > 0 && !scores) { set_error("null scores"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  if (tot > 0)
+    JB_CUDA(cudaMemcpy2DAsync(d->d_rows, sizeof(float) * d->row_stride, scores, sizeof(float) * d->S, sizeof(float) * d->S, tot, cudaMemcpyHostToDevice, d->stream));
+  return stream_advance(d, n_new, last, want_interim);
+}
+
+extern "C" int jb200_stream_restart(jb200_decoder *d, int stream) {
+  if (!d || !d->stream_mode || stream < 0 || stream >= d->st_n) { set_error("jb200_stream_restart: bad argument"); return JB200_ERR_ARG; }
+  JB_CUDA(cudaSetDevice(d->device));
+  if (d->st_started[stream] && !d->st_done[stream]) {
+    const size_t tot = (size_t)d->P.n_nodes;
+    fill_slots_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(d->P.slots + (size_t)stream * d->P.n_nodes, tot);
+    JB_LAUNCH_CHECK();
+    JB_CUDA(cudaStreamSynchronize(d->stream));
+  }
+  d->st_t[stream] = 0; d->st_started[stream] = 0; d->st_done[stream] = 0;
+  return JB200_OK;
+}
+
+extern "C" int jb200_stream_status(jb200_decoder *d, int stream, int32_t *frames_done, int32_t *alive, int32_t *ended) {
+  if (!d || !d->stream_mode || stream < 0 || stream >= d->st_n) { set_error("jb200_stream_status: bad argument"); return JB200_ERR_ARG; }
+  if (frames_done) *frames_done = d->st_t[stream];
+  if (alive) *alive = (!d->st_started[stream] || d->st_done[stream]) ? 1 : (d->h_state[stream].stopped < 0);
+  if (ended) *ended = d->st_done[stream];
+  return JB200_OK;
+}
+
+extern "C" int jb200_stream_partial(jb200_decoder *d, int stream, int32_t *words, int max_words, int32_t *n_words, float *score, int32_t *frame) {
+  if (!d || !d->stream_mode || stream < 0 || stream >= d->st_n || !n_words) { set_error("jb200_stream_partial: bad argument"); return JB200_ERR_ARG; }
+  if (!d->st_started[stream] || d->st_done[stream]) { *n_words = 0; if (score) *score = JB200_LOG_ZERO; if (frame) *frame = -1; return JB200_OK; }
+  const UttState &st = d->h_state[stream];
+  const int n = std::min(st.interim_nwords, std::max(max_words, 0));
+  for (int i = 0; i < n && words; i++) words[i] = d->h_interim_words[(size_t)stream * MAX_WORDS + i];
+  *n_words = words ? n : st.interim_nwords;
+  if (score) *score = st.interim_score;
+  if (frame) *frame = st.interim_frame;
+  return JB200_OK;
+}
+
+extern "C" int jb200_stream_result(jb200_decoder *d, int stream, const jb200_utt_result **utt, const jb200_atom **atoms, const int32_t **words) {
+  if (!d || !d->stream_mode || stream < 0 || stream >= d->st_n) { set_error("jb200_stream_result: bad argument"); return JB200_ERR_ARG; }
+  if (!d->st_done[stream]) { set_error("stream %d has not ended", stream); return JB200_ERR_ARG; }
+  if (utt) *utt = d->h_results + stream;
+  if (atoms) *atoms = d->h_atoms;        // index with utt->atom_offset, as for a batch
+  if (words) *words = d->h_words;        // index with utt->word_offset
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_pipeline_info(jb200_decoder *d, int32_t *n_slices, float *score_busy_ms) {
+  if (!d) { set_error("null decoder"); return JB200_ERR_ARG; }
+  if (n_slices) *n_slices = d->last_piped ? d->n_chunks : 1;
+  if (score_busy_ms) *score_busy_ms = d->last_piped ? d->last_score_busy_ms : 0.0f;
+  return JB200_OK;
+}
+
+extern "C" int jb200_decoder_set_pipeline(jb200_decoder *d, int frames_per_slice) {
+  if (!d || frames_per_slice < 0) { set_error("jb200_decoder_set_pipeline: bad argument"); return JB200_ERR_ARG; }
+  d->pipe_frames = frames_per_slice;
+  return JB200_OK;
 }
 
 extern "C" int jb200_decoder_results(jb200_decoder *d, const jb200_utt_result **utts, const jb200_atom **atoms, const int32_t **words) {

@@ -96,7 +96,8 @@ template <int D, bool EXACT, bool PRUNE>
 __global__ void __launch_bounds__(GMM_THREADS)
 gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles, int tiles_per_chunk, int n_tiles,
                  const float *__restrict__ feats, float *__restrict__ rows, int T, int row_stride,
-                 const float *__restrict__ tbl, int gprune_num) {
+                 const float *__restrict__ tbl, int gprune_num,
+                 const int *__restrict__ seg_off, const int *__restrict__ seg_start, int n_seg) {
   constexpr int STRIDE = gmm_stride(D);
   constexpr int NQ = STRIDE / 4;                 // float4 per record
   __shared__ __align__(128) float buf[2][GMM_TILE_GAUSS * STRIDE];
@@ -120,11 +121,20 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
   // this thread's frames, in registers
   float v[GMM_FPT][D];                       // scalar copy (pruned variant)
   unsigned long long v2[GMM_FPT][NQ];        // the same, packed (x_2q, x_2q+1) for the FFMA2 path
+  // T counts LOGICAL frames.  With a segment list (the batch pipeline scores one time slice of every utterance per
+  // launch) logical frame f is frame seg_start[s] + f - seg_off[s] of the feature / score matrices, s = its segment
   int fr[GMM_FPT];
 #pragma unroll
   for (int k = 0; k < GMM_FPT; k++) {
-    fr[k] = f0 + k * GMM_THREADS;
-    const float *src = feats + (size_t)min(fr[k], T - 1) * D;
+    const int fl = f0 + k * GMM_THREADS;
+    int fp = min(fl, T - 1);
+    if (seg_off != nullptr) {
+      int lo = 0, hi = n_seg;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(seg_off + mid) <= fp) lo = mid; else hi = mid; }
+      fp = __ldg(seg_start + lo) + (fp - __ldg(seg_off + lo));
+    }
+    fr[k] = (fl < T) ? fp : -1;                      // physical frame, -1 = padding lane
+    const float *src = feats + (size_t)fp * D;
 #pragma unroll
     for (int d = 0; d < D; d++) v[k][d] = __ldg(src + d);
 #pragma unroll
@@ -247,7 +257,7 @@ gmm_score_kernel(const float *__restrict__ pk, const GmmTile *__restrict__ tiles
       }
 #pragma unroll
       for (int k = 0; k < GMM_FPT; k++)
-        if (fr[k] < T) rows[(size_t)fr[k] * row_stride + tl.s0 + si] = res[k];
+        if (fr[k] >= 0) rows[(size_t)fr[k] * row_stride + tl.s0 + si] = res[k];
       grel += nm;
     }
     __syncthreads();   // everyone is done with buf[b] before it is refilled two tiles later
@@ -435,7 +445,8 @@ extern "C" int jb200_gmm_n_states(const jb200_gmm *h) { return h ? h->S : 0; }
 extern "C" int jb200_gmm_n_cdsets(const jb200_gmm *h) { return h ? h->C : 0; }
 
 template <int D>
-static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st) {
+static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st,
+                      const int *seg_off = nullptr, const int *seg_start = nullptr, int n_seg = 0) {
   const int fblocks = (T + GMM_THREADS * GMM_FPT - 1) / (GMM_THREADS * GMM_FPT);
   // enough CTAs for >= 2 waves of 4 CTAs/SM when the frame count alone does not provide them
   int want = h->sm_count * 8;
@@ -447,7 +458,7 @@ static int launch_gmm(jb200_gmm *h, const float *d_feats, int T, float *d_rows, 
   dim3 grid(fblocks, chunks);
   const bool prune = h->gprune_method != JB200_GPRUNE_NONE;
   const bool exact = h->mode == JB200_GMM_EXACT;
-#define JB_GO(E, P) gmm_score_kernel<D, E, P><<<grid, GMM_THREADS, 0, st>>>(h->d_pk, h->d_tiles, tiles_per_chunk, h->n_tiles, d_feats, d_rows, T, row_stride, h->d_tbl, h->gprune_num)
+#define JB_GO(E, P) gmm_score_kernel<D, E, P><<<grid, GMM_THREADS, 0, st>>>(h->d_pk, h->d_tiles, tiles_per_chunk, h->n_tiles, d_feats, d_rows, T, row_stride, h->d_tbl, h->gprune_num, seg_off, seg_start, n_seg)
   if (exact && !prune) JB_GO(true, false);
   else if (exact && prune) JB_GO(true, true);
   else if (!exact && !prune) JB_GO(false, false);
@@ -475,15 +486,17 @@ extern "C" int jb200_gmm_cdsets_device(jb200_gmm *h, float *d_rows, int T, void 
 
 namespace jb200 {
 // state columns only, caller-chosen row stride (used by the decoder, which evaluates cd sets on demand)
-int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st) {
+// seg_off/seg_start (device, n_seg entries, may be null): T logical frames gathered from segments of the matrices
+int gmm_launch_states(jb200_gmm *h, const float *d_feats, int T, float *d_rows, int row_stride, cudaStream_t st,
+                      const int *seg_off, const int *seg_start, int n_seg) {
   if (T <= 0) return JB200_OK;
   if (h->G == 0) { set_error("this scorer carries no Gaussians (DNN-HMM layout only)"); return JB200_ERR_ARG; }
   JB_CUDA(cudaSetDevice(h->device));
   switch (h->D) {
-    case 39: return launch_gmm<39>(h, d_feats, T, d_rows, row_stride, st);
-    case 38: return launch_gmm<38>(h, d_feats, T, d_rows, row_stride, st);
-    case 26: return launch_gmm<26>(h, d_feats, T, d_rows, row_stride, st);
-    case 25: return launch_gmm<25>(h, d_feats, T, d_rows, row_stride, st);
+    case 39: return launch_gmm<39>(h, d_feats, T, d_rows, row_stride, st, seg_off, seg_start, n_seg);
+    case 38: return launch_gmm<38>(h, d_feats, T, d_rows, row_stride, st, seg_off, seg_start, n_seg);
+    case 26: return launch_gmm<26>(h, d_feats, T, d_rows, row_stride, st, seg_off, seg_start, n_seg);
+    case 25: return launch_gmm<25>(h, d_feats, T, d_rows, row_stride, st, seg_off, seg_start, n_seg);
     default: set_error("feature dimension %d not instantiated (39, 38, 26, 25)", h->D); return JB200_ERR_UNSUPPORTED;
   }
 }
@@ -493,7 +506,7 @@ extern "C" int jb200_gmm_score_device(jb200_gmm *h, const float *d_feats, int T,
   if (!h || !d_feats || !d_rows) { set_error("jb200_gmm_score_device: null argument"); return JB200_ERR_ARG; }
   if (T <= 0) return JB200_OK;
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  int rc = gmm_launch_states(h, d_feats, T, d_rows, h->row_stride, st);
+  int rc = gmm_launch_states(h, d_feats, T, d_rows, h->row_stride, st, nullptr, nullptr, 0);
   if (rc) return rc;
   return jb200_gmm_cdsets_device(h, d_rows, T, st);
 }

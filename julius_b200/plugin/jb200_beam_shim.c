@@ -5,20 +5,28 @@
  * turns the stock Julius host into a front for the GPU path, jconf surface unchanged:
  *
  *   get_back_trellis_init(param, r)      beam.c:1825  bt_prepare and the per-utterance host state, as the original
- *   get_back_trellis_proceed(t, ...)     beam.c:2663  nothing to do per frame; returns TRUE, no interim result
- *   get_back_trellis_end(param, r)       beam.c:3052  param now holds ALL frames of the input in both of the host's
- *                                                    modes -- buffered (pass1.c:220-254 calls _init with the whole
- *                                                    utterance) and real-time (realtime-1stpass.c:681 calls _init with
- *                                                    ONE frame and grows param as audio arrives) -- so this is where
- *                                                    the utterance is scored and decoded on the GPU
- *                                                    (jb200_decode_batch_host) and r->backtrellis is materialised from
- *                                                    the GPU's atoms through bt_new/bt_store (backtrellis.c:154,190)
+ *   get_back_trellis_proceed(t, ...)     beam.c:2663  two modes.  Buffered (default for file input): nothing per frame.
+ *                                                    Frame-synchronous (real-time input, -progout, or JB200_STREAM=1):
+ *                                                    frame t has just arrived in param (realtime-1stpass.c:681 calls
+ *                                                    _init with ONE frame and grows param as audio comes in); the
+ *                                                    frames not yet decoded are fed to the device stream every
+ *                                                    JB200_STREAM_FRAMES frames (default 10 = 100 ms), and always when
+ *                                                    the host is due an interim result (beam.c:2983-2993: every
+ *                                                    progout_interval_frame frames r->result.pass1 gets the best word
+ *                                                    sequence so far and have_interim is raised); returns FALSE once
+ *                                                    the beam ran empty (beam.c:3012-3015)
+ *   get_back_trellis_end(param, r)       beam.c:3052  param now holds ALL frames of the input.  Buffered mode: this is
+ *                                                    where the utterance is scored and decoded on the GPU
+ *                                                    (jb200_decode_batch_host); frame-synchronous mode: the remaining
+ *                                                    frames go to the stream together with the end-of-utterance mark.
+ *                                                    Either way r->backtrellis is materialised from the GPU's atoms
+ *                                                    through bt_new/bt_store (backtrellis.c:154,190)
  *   finalize_1st_pass(r, len)            beam.c:3133  bt_relocate_rw + bt_sort_rw, then publishes the
  *                                                    pass-1 best exactly where find_1pass_result does
  *                                                    (beam.c:497-512)
  *   fsbeam_free(d)                       beam.c:3180
  * Restrictions (checked, fail loudly): N-gram LM, no short-pause segmentation, feature-vector input at least as wide
- * as the model's.  Progressive (interim) output is not produced: pass 1 runs when the input is complete.
+ * as the model's.
  * (normal and multipath trees both run on the device).  The models are flattened on first use with the same code as the plugin.
  */
 #include <julius/juliuslib.h>
@@ -46,6 +54,11 @@ typedef struct {
   jb200_gmm *gmm; jb200_dnn *dnn; jb200_decoder *dec;
   int max_frames, max_utts;
   boolean ok;            /* last decode succeeded */
+  /* frame-synchronous mode */
+  boolean streaming;     /* this utterance runs on a device stream */
+  int fed;               /* frames handed to the stream so far */
+  int stream_frames;     /* feed granularity */
+  float *stage; int stage_cap;   /* packing buffer for one feed */
   ShimResult cur;        /* result of the utterance being finished */
   /* decode-ahead over a file list (JB200_FILELIST = the list given to -filelist, JB200_AHEAD = how many files a batch) */
   char **files; int n_files, next_file;   /* next_file: index of the utterance the host will finish next */
@@ -134,11 +147,77 @@ boolean get_back_trellis_init(HTK_Param *param, RecogProcess *r) {
     jlog("ERROR: jb200: input vectors have %d components, the acoustic model takes %d\n", (int)param->veclen, s->gd.dim);
     return FALSE;
   }
+  /* frame-synchronous decoding when the input is live, when the host wants interim results, or on request */
+  {
+    const char *e = getenv("JB200_STREAM"), *f = getenv("JB200_STREAM_FRAMES");
+    /* live input: realtime-1stpass.c:681-682 hands _init the first frame alone (a RecogProcess has no way to ask its
+     * Recog for decodeopt.realtime_flag); a buffered one-frame input takes the same route, which is equally right */
+    const boolean live = (param->samplenum <= 1);
+    const int shift = (r->am != NULL && r->am->config != NULL) ? r->am->config->analysis.para.frameshift : 0;
+    s->streaming = (e != NULL) ? (atoi(e) != 0) : (live || r->config->output.progout_flag);
+    s->stream_frames = (f != NULL && atoi(f) > 0) ? atoi(f) : 10;
+    s->fed = 0;
+    if (s->streaming) {
+      /* live input has no length yet: room for the longest input the host accepts (MAXSPEECHLEN samples) */
+      int cap = (shift > 0) ? MAXSPEECHLEN / shift + 16 : 4096;
+      if (cap < param->samplenum) cap = param->samplenum;
+      s = shim_for(r, cap);
+      if (s == NULL) return FALSE;
+      if (g_api.stream_open(s->dec, 1) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); return FALSE; }
+    }
+  }
+  return TRUE;
+}
+
+/* hand frames [s->fed, upto) of param to the device stream */
+static boolean stream_push(Shim *s, HTK_Param *param, int upto, boolean last, boolean interim) {
+  const int D = s->gd.dim, n = upto - s->fed;
+  int32_t n_new = n; uint8_t fin = last ? 1 : 0;
+  int t;
+  if (n < 0) return FALSE;
+  if (n > s->stage_cap) {
+    free(s->stage);
+    s->stage_cap = n < 64 ? 64 : n;
+    s->stage = (float *)malloc(sizeof(float) * (size_t)s->stage_cap * D);
+    if (s->stage == NULL) { s->stage_cap = 0; jlog("ERROR: jb200: out of memory\n"); return FALSE; }
+  }
+  for (t = 0; t < n; t++) memcpy(s->stage + (size_t)t * D, param->parvec[s->fed + t], sizeof(float) * D);
+  if (g_api.stream_feed_host(s->dec, s->stage, &n_new, &fin, interim ? 1 : 0) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); return FALSE; }
+  s->fed = upto;
   return TRUE;
 }
 
 boolean get_back_trellis_proceed(int t, HTK_Param *param, RecogProcess *r, boolean final_for_multipath) {
+  Shim *s = shim_for(r, 0);
+  boolean want_interim;
   r->have_interim = FALSE;
+  if (s == NULL || !s->streaming || final_for_multipath) return TRUE;
+  /* beam.c:2983-2993: after frame t the best path ending at t-1 is published every progout_interval_frame frames */
+  want_interim = (t > 0 && r->config->output.progout_flag && r->config->output.progout_interval_frame > 0 &&
+                  ((t - 1) % r->config->output.progout_interval_frame) == 0);
+  if (t + 1 - s->fed < s->stream_frames && !want_interim) return TRUE;
+  if (!stream_push(s, param, t + 1, FALSE, want_interim)) return FALSE;
+  {
+    int32_t done = 0, alive = 1, ended = 0;
+    g_api.stream_status(s->dec, 0, &done, &alive, &ended);
+    if (!alive) {
+      jlog("ERROR: get_back_trellis_proceed: %02d %s: frame %d: no nodes left in beam, now terminates search\n", r->config->id, r->config->name, t);
+      return FALSE;
+    }
+  }
+  if (want_interim) {
+    int32_t words[MAXSEQNUM], nw = 0, frame = -1; float score = LOG_ZERO; int i;
+    if (g_api.stream_partial(s->dec, 0, words, MAXSEQNUM, &nw, &score, &frame) == 0) {
+      /* what bt_current_max leaves in r->result (beam.c:898-920) */
+      r->have_interim = TRUE;
+      r->result.status = J_RESULT_STATUS_SUCCESS;
+      r->result.num_frame = t - 1;
+      r->result.pass1.word_num = nw;
+      for (i = 0; i < nw; i++) r->result.pass1.word[i] = (WORD_ID)words[i];
+      if (nw > 0) { r->result.pass1.score = score; r->result.pass1.score_am = score; r->result.pass1.score_lm = 0.0; }
+      if (getenv("JB200_SHIM_VERBOSE")) { printf("JB200_SHIM interim t=%d words=%d score=%f\n", t, (int)nw, score); fflush(stdout); }
+    }
+  }
   return TRUE;
 }
 
@@ -266,6 +345,14 @@ void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
   if (s == NULL) return;
   s->ok = FALSE;
   if (T < 1 || param->is_outprob || param->veclen < s->gd.dim) return;       /* refused at _init already */
+  if (s->streaming) {
+    /* frame-synchronous mode: the rest of the input and the end-of-utterance mark */
+    const jb200_utt_result *u; const jb200_atom *a; const int32_t *w;
+    if (!stream_push(s, param, T, TRUE, FALSE)) return;
+    if (g_api.stream_result(s->dec, 0, &u, &a, &w) != 0 || result_copy(&s->cur, u, a, w) != 0) { jlog("ERROR: jb200: %s\n", g_api.last_error()); return; }
+    s->ok = TRUE; s->next_file++;
+    goto materialise;
+  }
   D = s->gd.dim;
   in = (float *)malloc(sizeof(float) * (size_t)T * D);
   if (in == NULL) { jlog("ERROR: jb200: out of memory\n"); return; }
@@ -293,6 +380,7 @@ void get_back_trellis_end(HTK_Param *param, RecogProcess *r) {
     s->ok = TRUE; s->n_single++;
   }
   free(in);
+materialise:
   if (s->cur.u.overflow) { jlog("ERROR: jb200: device work area overflow (code %d); pass 1 result dropped\n", s->cur.u.overflow); s->ok = FALSE; return; }
   idx = (TRELLIS_ATOM **)malloc(sizeof(void *) * (size_t)(s->cur.u.n_atoms + 1));
   for (i = 0; i < s->cur.u.n_atoms; i++) {
@@ -361,6 +449,7 @@ void fsbeam_free(FSBeam *d) {
     if (s->gmm) { g_api.gmm_destroy(s->gmm); s->gmm = NULL; }
     if (s->n_files > 0) jlog("STAT: jb200: %ld utterances answered from decode-ahead batches, %ld decoded singly\n", s->n_from_cache, s->n_single);
     ahead_clear(s); result_free(&s->cur);
+    free(s->stage); s->stage = NULL; s->stage_cap = 0;
     jb200_blob_free(&s->blob);
     s->r = NULL; s->max_frames = 0; s->ok = FALSE;
   }

@@ -23,6 +23,11 @@ typedef struct {
   int (*decode_batch_host)(jb200_decoder *, const float *, const int32_t *, int);
   int (*decoder_results)(jb200_decoder *, const jb200_utt_result **, const jb200_atom **, const int32_t **);
   void (*decoder_destroy)(jb200_decoder *);
+  int (*stream_open)(jb200_decoder *, int);
+  int (*stream_feed_host)(jb200_decoder *, const float *, const int32_t *, const uint8_t *, int);
+  int (*stream_status)(jb200_decoder *, int, int32_t *, int32_t *, int32_t *);
+  int (*stream_partial)(jb200_decoder *, int, int32_t *, int, int32_t *, float *, int32_t *);
+  int (*stream_result)(jb200_decoder *, int, const jb200_utt_result **, const jb200_atom **, const int32_t **);
   void (*gmm_destroy)(jb200_gmm *);
   void (*dnn_destroy)(jb200_dnn *);
 } jb200_api;
@@ -53,6 +58,11 @@ static int jb200_api_load(jb200_api *a, void *anchor) {
   JB200_SYM(decode_batch_host, "jb200_decode_batch_host");
   JB200_SYM(decoder_results, "jb200_decoder_results");
   JB200_SYM(decoder_destroy, "jb200_decoder_destroy");
+  JB200_SYM(stream_open, "jb200_stream_open");
+  JB200_SYM(stream_feed_host, "jb200_stream_feed_host");
+  JB200_SYM(stream_status, "jb200_stream_status");
+  JB200_SYM(stream_partial, "jb200_stream_partial");
+  JB200_SYM(stream_result, "jb200_stream_result");
   JB200_SYM(gmm_destroy, "jb200_gmm_destroy");
   JB200_SYM(dnn_destroy, "jb200_dnn_destroy");
 #undef JB200_SYM

@@ -166,6 +166,18 @@ static void on_result(Recog *recog, void *dummy) {
   fprintf(stdout, "\n");
 }
 
+/* progressive output (-progout): what bt_current_max left in r->result.pass1 (beam.c:876-921), every interval */
+static void on_interim(Recog *recog, void *dummy) {
+  RecogProcess *r = recog->process_list;
+  union { float f; unsigned u; } sc;
+  int i;
+  if (!r->have_interim) return;
+  sc.f = (r->result.pass1.word_num > 0) ? r->result.pass1.score : 0.0f;
+  fprintf(stdout, "JREF_INTERIM utt=%d frame=%d score=%08x words=", g_utt, r->result.num_frame, sc.u);
+  for (i = 0; i < r->result.pass1.word_num; i++) fprintf(stdout, "%s%d", i ? "," : "", (int)r->result.pass1.word[i]);
+  fprintf(stdout, "\n");
+}
+
 int main(int argc, char *argv[]) {
   Jconf *jconf;
   Recog *recog;
@@ -194,6 +206,7 @@ int main(int argc, char *argv[]) {
   callback_add(recog, CALLBACK_EVENT_PASS1_FRAME, on_pass1_frame, NULL);
   callback_add(recog, CALLBACK_EVENT_PASS1_END, on_pass1_end, NULL);
   if (getenv("JREF_RESULT")) callback_add(recog, CALLBACK_RESULT, on_result, NULL);
+  if (getenv("JREF_INTERIM")) callback_add(recog, CALLBACK_RESULT_PASS1_INTERIM, on_interim, NULL);
   if (j_adin_init(recog) == FALSE) return 1;
 
   if (jconf->input.speech_input == SP_MFCFILE || jconf->input.speech_input == SP_OUTPROBFILE) {

@@ -230,8 +230,21 @@ void oracle_set_heap_dump(const char *path) {
   if (path && path[0]) heap_dump_fp = fopen(path, "wb");
 }
 
+/* test tooling: oracle_set_node_dump(path) appends (totalnum, node ids of the frame's tokens in creation order) at
+   every beam cut -- the per-frame node working set, for tools/node_locality.py */
+static FILE *node_dump_fp = NULL;
+void oracle_set_node_dump(const char *path) {
+  if (node_dump_fp) { fclose(node_dump_fp); node_dump_fp = NULL; }
+  if (path && path[0]) node_dump_fp = fopen(path, "wb");
+}
+
 static void sort_token_no_order(Beam *b, int neednum, int *start, int *end) {
   int totalnum = b->tnum[b->tn], restnum = totalnum - neednum;
+  if (node_dump_fp) {
+    int i;
+    fwrite(&totalnum, sizeof(int), 1, node_dump_fp);
+    for (i = 0; i < totalnum; i++) fwrite(&b->tlist[b->tn][i].node, sizeof(int), 1, node_dump_fp);
+  }
   if (heap_dump_fp && neednum < totalnum) {
     int hdr[2] = { totalnum, neednum }, i;
     fwrite(hdr, sizeof(int), 2, heap_dump_fp);

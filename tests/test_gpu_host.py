@@ -132,3 +132,43 @@ def test_beam_shim_decode_ahead_over_a_file_list(tmp_path):
     for u, ref in zip(refdump.load_refdump(dump2), g.utts + g.utts):
         ok, why = atoms_equal(u.atoms, ref.atoms)
         assert ok, why
+
+
+@pytest.mark.parametrize("case", ["small_b100", "small_mp"])
+@pytest.mark.parametrize("frames", ["1", "7"])
+def test_stock_host_drives_the_gpu_beam_frame_by_frame(case, frames, tmp_path):
+    """Frame-synchronous mode of the beam shim (what real-time input and -progout select; forced here with
+    JB200_STREAM=1): get_back_trellis_proceed(t) feeds the frames that have arrived to a device stream
+    (jb200_stream_feed_host), get_back_trellis_end sends the rest with the end-of-utterance mark.  Same trellis and
+    pass-1 result as the stock host, whatever the feed size."""
+    from oracle import ffi
+    g, d, files = _prepare(case, tmp_path)
+    dump, out = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], binary=ffi.JREF_GPU,
+                            env_extra={"JB200_STREAM": "1", "JB200_STREAM_FRAMES": frames})
+    utts = refdump.load_refdump(dump)
+    assert len(utts) == len(g.utts)
+    for u, ref in zip(utts, g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.status == ref.status
+        assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+
+
+@pytest.mark.parametrize("case", ["small_b100", "small_mp"])
+def test_progressive_output_matches_the_stock_host(case, tmp_path):
+    """-progout: every -proginterval the host publishes the best word sequence so far (bt_current_max, beam.c:876-921,
+    raised through have_interim / CALLBACK_RESULT_PASS1_INTERIM, pass1.c:306-314).  The GPU beam must hand the host the
+    same interim sequences and scores, at the same frames, as the stock beam -- and the same final trellis."""
+    from oracle import ffi
+    g, d, files = _prepare(case, tmp_path)
+    extra = g.meta["extra_args"] + ["-progout", "-proginterval", "100"]
+    _, stock = ffi.run_ref(d, files, extra_args=extra, dump="stock.jrf", env_extra={"JREF_INTERIM": "1"})
+    want = [ln for ln in stock.splitlines() if ln.startswith("JREF_INTERIM")]
+    assert len(want) >= 10 * len(files) and any("words=0," in w for w in want)
+    dump, out = ffi.run_ref(d, files, extra_args=extra, binary=ffi.JREF_GPU, env_extra={"JREF_INTERIM": "1"})
+    got = [ln for ln in out.splitlines() if ln.startswith("JREF_INTERIM")]
+    assert got == want
+    for u, ref in zip(refdump.load_refdump(dump), g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
