@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.used,memory.total --format=csv
+free -g | head -2
+( time timeout 420 python tools/exp_pipeline.py tri20k 3 ) > gpurun_out/exp_pipeline.txt 2> gpurun_out/exp_pipeline.err; cat gpurun_out/exp_pipeline.txt; tail -5 gpurun_out/exp_pipeline.err
+( time timeout 400 python -m pytest tests/test_gpu_stream.py tests/test_gpu_beam.py -m gpu -q -x --durations=8 ) > gpurun_out/pytest_a.txt 2>&1; tail -25 gpurun_out/pytest_a.txt
+( time timeout 300 python -m pytest tests/test_gpu_host.py -m gpu -q --durations=8 -k "frame_by_frame or progressive or linked_in" ) > gpurun_out/pytest_b.txt 2>&1; tail -25 gpurun_out/pytest_b.txt

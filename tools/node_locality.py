@@ -13,7 +13,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from julius_b200 import desc as D, refdump, workload, renumber
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import renumber_proto as renumber
+from julius_b200 import desc as D, refdump, workload
 from oracle import ffi
 
 

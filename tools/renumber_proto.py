@@ -1,11 +1,14 @@
-"""Prototype (analysis only, used by tools/node_locality.py): renumberings of the lexicon tree that keep every
-`next_a` chain (node, node+1, ...) consecutive.  The product's renumbering lives in csrc/beam.cu (decoder create)."""
+"""Prototype (analysis only, used by tools/node_locality.py): renumberings of the lexicon tree.
+  bfs / depth_lm : keep every `next_a` chain (node, node+1, ...) consecutive -- on the synthetic 20k-word tree a chain is
+                   a whole word, so these cannot separate the tree's levels and gain nothing;
+  bfs_free       : plain breadth-first order from the roots (needs an explicit successor in the node record) -- what
+                   jb200_decoder_create does (csrc/beam.cu)."""
 from __future__ import annotations
 
 import numpy as np
 
 LOG_ZERO = -1000000.0
-MODES = ("bfs", "depth_lm")
+MODES = ("bfs", "depth_lm", "bfs_free")
 
 
 def chains(blob):
@@ -20,8 +23,34 @@ def chains(blob):
     return heads, chain_of, length
 
 
+def bfs_free(blob) -> np.ndarray:
+    n = int(blob["tree.n_nodes"][0])
+    next_a, arc_off, arc_to = blob["tree.next_a"], blob["tree.arc_off"], blob["tree.arc_to"]
+    seen = np.zeros(n, bool)
+    order = []
+    def push(x):
+        if not seen[x]:
+            seen[x] = True; order.append(x)
+    for r in list(blob["tree.iso_node"]) + list(blob["tree.shared_node"]):
+        push(int(r))
+    i = 0
+    while i < len(order):
+        x = order[i]; i += 1
+        if next_a[x] != np.float32(LOG_ZERO) and x + 1 < n:
+            push(x + 1)
+        for k in arc_to[arc_off[x]:arc_off[x + 1]].tolist():
+            push(k)
+    for x in range(n):
+        push(x)
+    perm = np.empty(n, np.int32)
+    perm[np.array(order)] = np.arange(n, dtype=np.int32)
+    return perm
+
+
 def permutation(blob, mode: str) -> np.ndarray:
     n = int(blob["tree.n_nodes"][0])
+    if mode == "bfs_free":
+        return bfs_free(blob)
     heads, chain_of, length = chains(blob)
     nc = len(heads)
     arc_off, arc_to = blob["tree.arc_off"], blob["tree.arc_to"]
