@@ -205,7 +205,7 @@ def run_reference(workload_name: str, n_procs: int, n_timed: int, n_frames: int,
     for p in procs:
         out = p.stdout.read()
         p.wait()
-        last_out = out
+        last_out = f"[exit code {p.returncode}] " + out
         fr, sec = 0, 0.0
         for line in out.splitlines():
             if line.startswith("JREF_UTT"):
@@ -317,7 +317,10 @@ def fp32_peak():
     return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 figure in MEASURED_PEAKS.json)"
 
 
-PIPE_FRAMES_DEFAULT = 0       # set from the round's measurements, see DESIGN.md K3/K1 "batch pipeline"
+# frames per time slice of the batch pipeline for GMM workloads ("batch pipeline"): measured on tri20k,
+# 444 utterances (profiles/exp_r02_slices.txt): 1.391 M frames/s with 96-frame slices, 1.432 M with 64, 1.430 M with 48,
+# 1.446 M with 32 (one launch per batch at 592 utterances: 1.357 M)
+PIPE_FRAMES_DEFAULT = 32
 
 
 def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True, n_batches=2, seed0=100, pipe_frames=0):
@@ -345,7 +348,10 @@ def measure_workload(ctx, name, B, T, steps, warmup, mode="exact", want_e2e=True
     probe = capi.Decoder(ds, am, max_utts=1, max_frames=8)
     resident = max(1, probe.resident_utts())       # one resident wave of thread blocks
     probe.close()
-    pipe = 0 if use_dnn else max(0, pipe_frames)
+    # the pipeline pays off where a K1 block beside three beam blocks beats a fourth beam block: GMM scoring on normal trees
+    # (measured: tri20k +7 %, tri20k_gbeam +29 %; the multipath kernel loses more from the missing block than the overlap
+    # returns: tri20k_mp 0.69 M sliced at 444 utterances against 0.79 M unsliced at 592)
+    pipe = 0 if (use_dnn or int(ds.tree.multipath)) else max(0, pipe_frames)
     if not B:
         # the pipeline needs room for one scoring thread block beside the beam's on every SM: 3/4 of a resident wave
         B = (resident * 3) // 4 if pipe else resident
@@ -599,6 +605,16 @@ def product_main(a):
             q = measure_workload(ctx, a.workload, b, T, 3, 2, mode=a.mode, want_e2e=True)
             extra[tag] = {"utterances": b, "frames_per_utt": T, "ms_device": q["dev_ms"] / q["steps"], "ms_e2e": q["e2e_ms"] / q["steps"],
                           "frames_per_s_e2e": b * T * q["steps"] / (q["e2e_ms"] / 1000.0)}
+        if r["pipe_slices"] > 1:
+            # the same workload, one scoring launch then one beam launch per batch at a full resident wave: the kernels'
+            # durations ALONE (in the sliced headline run they overlap and slow each other down)
+            q = measure_workload(ctx, a.workload, r["resident"], T, 3, 2, mode=a.mode, want_e2e=False, pipe_frames=0)
+            qroof, qscoring = rooflines(q, world)
+            extra["unsliced"] = {"utts_per_gpu": q["B"], "frames_per_utt": T, "value": q["B"] * T * q["steps"] / (q["wall_ms"] / 1000.0),
+                                 "unit": "frames/s", "ms_per_step": q["wall_ms"] / q["steps"], "kernel_ms": qroof["kernel_ms"],
+                                 "roofline": {k: qroof[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "algorithmic_bytes")},
+                                 "roofline_scoring": {k: qscoring[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "ms")},
+                                 "beam_phase_cycles_per_frame": qroof["beam_phase_cycles_per_frame"], "decoded_ok": f"{q['n_ok']}/{q['n_res']}"}
         if host_shim is not None:
             extra["host_shim"] = host_shim
         # K2 on the driver's record: a short leg of the DNN-HMM workload (BASELINE configs[3]) unless it is the headline
@@ -618,6 +634,11 @@ def product_main(a):
         value = frames_total / (r["wall_ms"] / 1000.0)
         e2e = frames_total / (r["e2e_ms"] / 1000.0)
         roof, scoring = rooflines(r, world)
+        if "unsliced" in extra:
+            roof["alone"] = {"note": "the same kernel timed without the scoring kernel beside it (leg `unsliced`, %d utterances)" % extra["unsliced"]["utts_per_gpu"],
+                             **{k: extra["unsliced"]["roofline"][k] for k in ("achieved", "frac")},
+                             "ms": extra["unsliced"]["kernel_ms"].get(roof["kernel"])}
+            scoring["alone"] = {k: extra["unsliced"]["roofline_scoring"][k] for k in ("achieved", "frac", "ms")}
         line = {
             "metric": "frames/sec (xRT) 20k-word triphone decode", "value": value, "unit": "frames/s", "xRT": value / 100.0,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["wall_ms"] / a.steps, "device_event_ms_per_step": r["dev_ms"] / a.steps,

@@ -208,9 +208,26 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
     }
     if (w->dfa_forward != NULL) { jlog("ERROR: jb200: forward-DFA state tracking (.dfa.forward) is not supported\n"); return -1; }
   } else {
-    if (w->lmtype != LM_PROB || ng == NULL) { jlog("ERROR: jb200: lexicon tree without a language model\n"); return -1; }
+    if (w->lmtype != LM_PROB || (ng == NULL && w->lmvar != LM_NGRAM_USER)) { jlog("ERROR: jb200: lexicon tree without a language model\n"); return -1; }
     if (w->category_tree) { jlog("ERROR: jb200: category tree with an N-gram is not supported\n"); return -1; }
-    if (w->lmvar == LM_NGRAM_USER) { jlog("ERROR: jb200: user-defined LM functions are not supported\n"); return -1; }
+    if (w->lmvar == LM_NGRAM_USER) {
+      /* -userlm (wchmm.h:274-276): pass 1 reads the LM through two host function pointers.  They cannot be called from
+       * the device, so the 2-gram side is tabulated once -- a dense table over the dictionary, see below -- which bounds
+       * the vocabulary this mode supports */
+      const char *e = getenv("JB200_USERLM_MAXWORDS");
+      const int lim = (e != NULL && atoi(e) > 0) ? atoi(e) : 8192;
+      if (w->bi_prob_user == NULL) { jlog("ERROR: jb200: -userlm without a registered 2-gram function\n"); return -1; }
+      if (ng != NULL) {
+        /* the host caches these values per N-gram entry of the last word (factoring_sub.c:951-957,966: last_nword), so
+         * with two dictionary words on one entry what it returns depends on which of them asked first */
+        unsigned char *seen = (unsigned char *)calloc((size_t)ng->max_word_num + 1, 1);
+        int dup = 0;
+        for (i = 0; i < V && seen != NULL; i++) { if (seen[wi->wton[i]]) dup = 1; seen[wi->wton[i]] = 1; }
+        free(seen);
+        if (dup) { jlog("ERROR: jb200: -userlm with several dictionary words on one N-gram entry is not supported\n"); return -1; }
+      }
+      if (V > lim) { jlog("ERROR: jb200: -userlm is tabulated densely and supports up to %d words (JB200_USERLM_MAXWORDS), the dictionary has %d\n", lim, V); return -1; }
+    }
   }
 
   /* ---- arcs (A_CELL2 lists, kept in the order beam_intra_word walks them, beam.c:2172-2176) */
@@ -349,6 +366,8 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
 #ifdef CLASS_NGRAM
       cprob[i] = wi->cprob[i];
 #endif
+      /* -userlm: the tabulated values below are indexed by dictionary word and already final (x + 0.0f == x) */
+      if (!is_dfa && w->lmvar == LM_NGRAM_USER) { wton[i] = i; cprob[i] = 0.0f; }
     }
     jb200_blob_add(b, "tree.wordend_a", JB200_F32, V, wea);
     jb200_blob_add(b, "tree.wordend", JB200_I32, V, wend);
@@ -423,8 +442,48 @@ static int flatten_tree(RecogProcess *r, CdReg *cd, jb200_blob *b) {
     free(scw);
   }
 
-  /* ---- LM: the 1-/2-gram tables bi_prob_*() reads (ngram_access.c:249-466) */
-  {
+  /* ---- LM */
+  if (w->lmvar == LM_NGRAM_USER) {
+    /* User-defined LM.  What pass 1 asks of it (factoring_sub.c:963-981 for a node with one successor word, :1118-1128
+     * for the isolated roots) is  g(lw, w) = bi_prob_user(winfo, lw, w, ngram 2-gram(lw, w) + cprob[w])  with LOG_ZERO in
+     * place of the N-gram term when no N-gram is loaded; the 1-gram factoring values (wchmm->fscore, above) went through
+     * uni_prob_user when the host built the tree (wchmm.c:1497,1626).  g is tabulated as a DENSE 2-gram over the dictionary
+     * itself: every row holds all V words, so the device's binary search always hits and returns the entry unchanged. */
+    const int64_t VV = (int64_t)V * V;
+    float *g = (float *)malloc(sizeof(float) * (size_t)VV), *zf = (float *)calloc((size_t)V, sizeof(float));
+    int *bw = (int *)malloc(sizeof(int) * (size_t)VV), *bgn = (int *)malloc(sizeof(int) * V), *num = (int *)malloc(sizeof(int) * V);
+    int a, c;
+    if (!g || !zf || !bw || !bgn || !num) { jlog("ERROR: jb200: out of memory tabulating the user LM\n"); return -1; }
+    for (a = 0; a < V; a++) {
+      bgn[a] = a * V; num[a] = V;
+      for (c = 0; c < V; c++) {
+        LOGPROB p;
+        if (ng != NULL) {
+          p = (*(ng->bigram_prob))(ng, wi->wton[a], wi->wton[c])
+#ifdef CLASS_NGRAM
+            + wi->cprob[c]
+#endif
+            ;
+        } else p = LOG_ZERO;
+        g[(size_t)a * V + c] = (*(w->bi_prob_user))(wi, (WORD_ID)a, (WORD_ID)c, p);
+        bw[(size_t)a * V + c] = c;
+      }
+    }
+    jb200_blob_add_i(b, "tree.lm_nvocab", V);
+    jb200_blob_add_i(b, "tree.lm_nbigram", (int)VV);
+    jb200_blob_add_i(b, "tree.lm_mode", JB200_BI_NORMAL);
+    jb200_blob_add_i(b, "tree.lm_unk_id", -1);
+    jb200_blob_add_f(b, "tree.lm_unk_num_log", 0.0f);
+    jb200_blob_add(b, "tree.uni_prob", JB200_F32, V, zf);
+    jb200_blob_add(b, "tree.uni_bow", JB200_F32, V, zf);
+    jb200_blob_add(b, "tree.bi_bgn", JB200_I32, V, bgn);
+    jb200_blob_add(b, "tree.bi_num", JB200_I32, V, num);
+    jb200_blob_add(b, "tree.bi_wid", JB200_I32, VV, bw);
+    jb200_blob_add(b, "tree.bi_prob", JB200_F32, VV, g);
+    jb200_blob_add_i(b, "tree.lm_user", 1);
+    free(g); free(zf); free(bw); free(bgn); free(num);
+  } else {
+    /* the 1-/2-gram tables bi_prob_*() reads (ngram_access.c:249-466) */
     NGRAM_TUPLE_INFO *t1 = &ng->d[0], *t2 = &ng->d[1];
     int Vn = ng->max_word_num, mode;
     const float *bow, *biprob;

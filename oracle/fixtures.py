@@ -18,7 +18,8 @@ from . import ffi
 
 
 def make_fixture(preset, outdir: str, n_utts: int = 2, n_frames: int = 200, seed: int = 11,
-                 extra_args: list = (), tokens: bool = False, noise_utts: int = 0, model=None, grammar: bool = False):
+                 extra_args: list = (), tokens: bool = False, noise_utts: int = 0, model=None, grammar: bool = False,
+                 env_extra: dict | None = None):
     """grammar=True: decode with the synthetic finite-state grammar (-dfa/-v) instead of the N-gram; the sampled
     utterances then follow sentences of that grammar."""
     cfg = synth.SynthConfig.preset(preset) if isinstance(preset, str) else preset
@@ -44,5 +45,5 @@ def make_fixture(preset, outdir: str, n_utts: int = 2, n_frames: int = 200, seed
     with open(os.path.join(outdir, "list.txt"), "w") as f:
         f.write("\n".join(files) + "\n")
     dump, out = ffi.run_ref(outdir, files, extra_args=extra_args, export=os.path.join(outdir, "model.jb2m"),
-                            tokens=tokens, lm_args=lm_args)
+                            tokens=tokens, lm_args=lm_args, env_extra=env_extra)
     return m, files, dump, out

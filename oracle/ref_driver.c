@@ -166,6 +166,18 @@ static void on_result(Recog *recog, void *dummy) {
   fprintf(stdout, "\n");
 }
 
+/* -userlm: a deterministic user-defined language model on top of (or instead of) the N-gram, registered the way
+   julius/main.c:153-161 does (JREF_USERLM=1 together with the -userlm option) */
+static LOGPROB my_uni(WORD_INFO *winfo, WORD_ID w, LOGPROB ngram_prob) {
+  return ngram_prob * 0.8f - 0.01f * (float)(w % 13);
+}
+static LOGPROB my_bi(WORD_INFO *winfo, WORD_ID context, WORD_ID w, LOGPROB ngram_prob) {
+  return ngram_prob * 0.9f - 0.02f * (float)(((int)context * 7 + (int)w * 3) % 11);
+}
+static LOGPROB my_lm(WORD_INFO *winfo, WORD_ID *contexts, int context_len, WORD_ID w, LOGPROB ngram_prob) {
+  return ngram_prob;
+}
+
 /* progressive output (-progout): what bt_current_max left in r->result.pass1 (beam.c:876-921), every interval */
 static void on_interim(Recog *recog, void *dummy) {
   RecogProcess *r = recog->process_list;
@@ -200,6 +212,16 @@ int main(int argc, char *argv[]) {
 
   jconf = j_config_load_args_new(nargs, args);
   if (jconf == NULL) return 1;
+  if (getenv("JREF_USERLM")) {
+    /* j_create_instance_from_jconf in its three steps, with the user LM registered between loading and fusion */
+    PROCESS_LM *lm;
+    if (j_jconf_finalize(jconf) == FALSE) return 1;
+    recog = j_recog_new();
+    recog->jconf = jconf;
+    if (j_load_all(recog, jconf) == FALSE) { fprintf(stderr, "jref: error in loading model\n"); return 1; }
+    for (lm = recog->lmlist; lm; lm = lm->next) if (lm->lmtype == LM_PROB) j_regist_user_lm_func(lm, my_uni, my_bi, my_lm);
+    if (j_final_fusion(recog) == FALSE) { fprintf(stderr, "jref: error in startup\n"); return 1; }
+  } else
   recog = j_create_instance_from_jconf(jconf);
   if (recog == NULL) { fprintf(stderr, "jref: error in startup\n"); return 1; }
   callback_add(recog, CALLBACK_EVENT_PASS1_BEGIN, on_pass1_begin, NULL);

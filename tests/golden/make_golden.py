@@ -42,7 +42,11 @@ CASES = {
     "small_tm": ("small_tm", 2, 200, 1, ["-gprune", "safe", "-tmix", "4", "-b", "100"]),
     # grammar mode (category tree + category-pair constraint, beam.c:1669-1760, :2404-2455), BASELINE configs[0] flavour
     "small_dfa": ("small", 2, 200, 1, ["-b", "80", "-penalty1", "-1.0"]),
+    # user-defined LM functions on top of the N-gram (-userlm, wchmm.h:274-276; registered by the driver, JREF_USERLM=1)
+    "small_userlm": ("small", 2, 200, 1, ["-userlm", "-b", "100"]),
 }
+# cases that need something in the driver's environment
+CASE_ENV = {"small_userlm": {"JREF_USERLM": "1"}}
 # DNN-HMM: (preset, DnnConfig kwargs, n_utts, n_frames, extra args)
 DNN_CASES = {
     "small_dnn": ("small", dict(in_dim=120, feature_len=40, context_len=3, hidden=128, layers=3), 2, 150, ["-b", "150"]),
@@ -60,7 +64,7 @@ def main():
             continue
         tmp = tempfile.mkdtemp(prefix="jb200_golden_")
         m, files, dump, out = fixtures.make_fixture(preset, tmp, n_utts=nu, n_frames=nf, noise_utts=nn, extra_args=extra,
-                                                    grammar=name in GRAMMAR_CASES)
+                                                    grammar=name in GRAMMAR_CASES, env_extra=CASE_ENV.get(name))
         dst = os.path.join(HERE, name)
         os.makedirs(dst, exist_ok=True)
         shutil.copy(os.path.join(tmp, "model.jb2m"), dst)
@@ -68,7 +72,7 @@ def main():
         feats = {f"u{i}": synth.read_htk_param(fn)[0] for i, fn in enumerate(files)}
         np.savez_compressed(os.path.join(dst, "feats.npz"), **feats)
         with open(os.path.join(dst, "meta.json"), "w") as f:
-            json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "grammar": name in GRAMMAR_CASES,
+            json.dump({"preset": preset, "extra_args": extra, "n_utts": len(files), "grammar": name in GRAMMAR_CASES, "env": CASE_ENV.get(name, {}),
                        "summary": out.strip().splitlines()[-1]}, f, indent=1)
         shutil.rmtree(tmp)
         print(name, "->", dst)

@@ -172,3 +172,21 @@ def test_progressive_output_matches_the_stock_host(case, tmp_path):
         ok, why = atoms_equal(u.atoms, ref.atoms)
         assert ok, why
         assert u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+
+
+def test_user_defined_lm_through_the_gpu_beam(tmp_path):
+    """-userlm (wchmm.h:274-276): the application registers LM functions (the driver does, JREF_USERLM=1, the way
+    julius/main.c:153-161 does); pass 1 reads them through two host function pointers, which the export step tabulates
+    for the device.  The stock host with the GPU beam linked in must produce the stock host's trellis."""
+    from oracle import ffi
+    g, d, files = _prepare("small_userlm", tmp_path)
+    dump, out = ffi.run_ref(d, files, extra_args=g.meta["extra_args"], binary=ffi.JREF_GPU, env_extra=g.meta["env"])
+    utts = refdump.load_refdump(dump)
+    assert len(utts) == len(g.utts)
+    for u, ref in zip(utts, g.utts):
+        ok, why = atoms_equal(u.atoms, ref.atoms)
+        assert ok, why
+        assert u.status == ref.status and u.words == ref.words and np.float32(u.score) == np.float32(ref.score)
+    # and the user LM really is in effect: the plain N-gram run of the same input scores differently
+    plain = Golden("small_b100")
+    assert np.float32(plain.utts[0].score) != np.float32(g.utts[0].score)

@@ -7,7 +7,8 @@ from julius_b200 import desc, refdump
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["tiny", "small_b100", "small_safe", "small_mp", "small_iwsp"]
+# small_userlm: user-defined LM functions (-userlm) on top of the N-gram, tabulated by the exporter
+CASES = ["tiny", "small_b100", "small_safe", "small_mp", "small_iwsp", "small_userlm"]
 DNN_CASES = ["small_dnn", "small_dnn_iwsp"]
 # pinned on the CPU only so far (the GPU suite does not run them yet)
 ORACLE_ONLY_CASES = ["small_tr", "small_tm", "small_dfa"]
