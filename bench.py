@@ -503,6 +503,7 @@ def rooflines(r, world):
             "beam_tokens_per_frame": r["tokens_per_frame"], "beam_created_per_frame": r["created_per_frame"],
             "beam_cut": {"upward_selects": hs["upward_selects"], "closed_form": hs["closed_form"],
                          "closed_form_frac": round(hs["closed_form"] / max(hs["upward_selects"], 1), 4),
+                         "closed_form_with_relocations": hs.get("closed_form_relocated", 0),
                          "replayed_extractions": hs["extractions"],
                          "replay_ticks_per_extraction": round(hs["levels"] / max(hs["extractions"], 1), 3)}}
     if r["use_dnn"]:

@@ -155,6 +155,8 @@ int jb200_decoder_heap_stats(jb200_decoder *d, int64_t out[3]);
 /* beam cuts that select the top of the token set (sort_token_upward) since create: out[0] how many,
  * out[1] how many of them were answered by the closed form (score, pre-order position) instead of a replay */
 int jb200_decoder_select_stats(jb200_decoder *d, int64_t out[2]);
+/* of the closed-form answers, how many needed the exact treatment of re-inserted elements (closed form with relocations) */
+int64_t jb200_decoder_relocated_selects(jb200_decoder *d);
 /* how many utterances (thread blocks) are co-resident on the device for this decoder */
 int jb200_decoder_resident_utts(const jb200_decoder *d);
 /* SM-cycle totals per kernel phase of the first n_utts utterances of the last batch: cycles [n_utts][8]

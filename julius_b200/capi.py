@@ -73,6 +73,8 @@ def lib():
             L.jb200_decoder_misspeculations.restype = C.c_int64
             L.jb200_decoder_heap_stats.argtypes = [vp, C.POINTER(C.c_int64)]
             L.jb200_decoder_select_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+            L.jb200_decoder_relocated_selects.argtypes = [vp]
+            L.jb200_decoder_relocated_selects.restype = C.c_int64
             L.jb200_decoder_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
             U8 = C.POINTER(C.c_uint8)
             L.jb200_decoder_set_pipeline.argtypes = [vp, C.c_int]
@@ -324,7 +326,8 @@ class Decoder:
         w = (C.c_int64 * 2)()
         _check(lib().jb200_decoder_select_stats(self._h, w), "jb200_decoder_select_stats")
         return {"fallbacks": int(v[0]), "levels": int(v[1]), "extractions": int(v[2]),
-                "upward_selects": int(w[0]), "closed_form": int(w[1])}
+                "upward_selects": int(w[0]), "closed_form": int(w[1]),
+                "closed_form_relocated": int(lib().jb200_decoder_relocated_selects(self._h))}
 
     def resident_utts(self) -> int:
         return int(lib().jb200_decoder_resident_utts(self._h))

@@ -130,6 +130,7 @@ struct BeamParams {
   const uint8_t *cp_allowed; const int *init_node; const float *init_lscore; int n_init; float penalty1;
   // chunked launches
   const ChunkDesc *chunk; UttState *state; int interim; int *interim_words;   // [n_utts][MAX_WORDS]
+  int no_reloc;             // JB200_NO_RELOCATE=1: replay the loop whenever the plain closed form's test fails (A/B)
   int atoms_in_place;       // streams: the finalized atoms of utterance u go to atoms_out + atom_off[u] (no batch compaction)
 };
 
@@ -665,16 +666,149 @@ __device__ __forceinline__ int closed_subtree_size(const int c, const int n, con
   const int first = c << sh, width = 1 << sh;
   return (width - 1) + max(0, min(n - first + 1, width));
 }
+
+// ---- the closed form WITH re-insertions ----------------------------------------------------------------------------
+// While every extraction's s is a loser the heap evolves by pull-ups and
+//   (I)  slot x holds the best remaining element of subtree(x) that no ancestor of x holds,
+// "best" = (score descending, pre-order position of the element's HOME slot ascending) -- which is also the extraction
+// order.  A tail leaf that still holds a candidate when it is taken breaks the pure pull-up picture: the element is
+// re-inserted from the root and lands on the chain of larger children where its score says, ABOVE whatever it ties with.
+// (I) survives if the element's home moves to where it lands (it is at least as good as both sub-trees below it).  So the
+// sorted candidate keys ARE the heap: for every flagged tail slot m, high slots first (step k = n-m+1),
+//   * who sits in leaf m: walk the alive part of the order (index >= k-1) and hand out the levels of the path root..m --
+//     level j goes to the first unused element whose home lies in subtree(a_j) (nested intervals of pre-order
+//     positions); m holds a candidate iff level depth(m) gets one;
+//   * where that element e lands: walk the order behind the root; the first element of subtree(x) is the occupant of the
+//     larger child of x (the left one on a tie: that is the order); e stays at x if its score is >= that element's
+//     ("STVAL >= SVAL(child)", beam.c:1362), else the hole moves into the child whose subtree holds that element's home;
+//   * e's key gets the landing slot's pre-order position and moves to its place in the order (behind this step's root).
+// tools/heapdyn.cpp is the CPU model (closed_dynamic_scan), exact on recorded cuts of real decodes and on random heaps
+// with as few as 8 distinct scores.  One warp; returns 0 on anything unexpected (the caller replays the loop instead).
+__device__ __noinline__ int closed_relocate(unsigned long long *keys, const int nc, const int n, const int need, unsigned *flags, const int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int H = 31 - __clz(n);
+  const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
+  for (int w = fwords - 1; w >= 0; w--) {
+    unsigned bits = flags[w];
+    while (bits) {
+      const int b = 31 - __clz(bits);
+      const int m = tail0 + w * 32 + b;
+      const int k = n - m + 1;                              // step; this step's root is keys[k-1]
+      if (m <= n && m >= 2 && k <= need) {
+        const int dm = 31 - __clz(m);
+        // --- the occupant of leaf m
+        int j = 0, a = 1, lo = 0, hi = n, occ = -1;
+        for (int base = k - 1; base < nc && occ < 0; base += 32) {
+          const int idx = base + lane;
+          const unsigned long long key = (idx < nc) ? keys[idx] : 0ull;
+          const int pre = 0xffff - (int)((key >> 16) & 0xffffu);
+          unsigned done = 0u;
+          while (true) {
+            const bool in = (idx < nc) && pre >= lo && pre < hi && !((done >> lane) & 1u);
+            const unsigned mask = __ballot_sync(FULL, in);
+            if (!mask) break;
+            const int f = __ffs(mask) - 1;
+            if (j == dm) { occ = base + f; break; }
+            j++;
+            const int nxt = m >> (dm - j);
+            const int lsz = closed_subtree_size(2 * a, n, H);
+            if (nxt == 2 * a) { lo = lo + 1; hi = lo + lsz; } else { lo = lo + 1 + lsz; }
+            a = nxt;
+            done |= (f >= 31) ? FULL : ((2u << f) - 1u);
+          }
+        }
+        if (occ >= k) {
+          // --- e = keys[occ] is re-inserted from the root of the heap of m-1 slots
+          __syncwarp();
+          const unsigned long long ekey = keys[occ];
+          const unsigned esc = (unsigned)(ekey >> 32);
+          const int msz = m - 1;
+          int x = 1; lo = 0; hi = n;
+          bool stop = (2 * x > msz);
+          for (int base = k; base < nc && !stop; base += 32) {
+            const int idx = base + lane;
+            const unsigned long long key = (idx < nc) ? keys[idx] : 0ull;
+            const int pre = 0xffff - (int)((key >> 16) & 0xffffu);
+            unsigned done = 0u;
+            while (!stop) {
+              const bool in = (idx < nc) && idx != occ && pre >= lo && pre < hi && !((done >> lane) & 1u);
+              const unsigned mask = __ballot_sync(FULL, in);
+              if (!mask) break;
+              const int f = __ffs(mask) - 1;
+              const unsigned osc = __shfl_sync(FULL, (unsigned)(key >> 32), f);
+              const int opre = __shfl_sync(FULL, pre, f);
+              if (opre == lo) return 0;                     // an unplaced element whose home is x: cannot happen
+              if (esc >= osc) { stop = true; break; }        // e stays at x
+              const int lsz = closed_subtree_size(2 * x, n, H);
+              if (opre < lo + 1 + lsz) { x = 2 * x; lo = lo + 1; hi = lo + lsz; }
+              else { x = 2 * x + 1; lo = lo + 1 + lsz; }
+              if (2 * x > msz) { stop = true; break; }
+              done |= (f >= 31) ? FULL : ((2u << f) - 1u);
+            }
+          }
+          // --- e's home is x (pre-order position lo): new key, new place among the alive elements behind this step's root
+          const unsigned long long nkey = (ekey & 0xffffffff0000ffffull) | ((unsigned long long)(0xffffu - (unsigned)lo) << 16);
+          int cnt = 0;
+          for (int base = k; base < nc; base += 32) {
+            const int idx = base + lane;
+            const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
+            const unsigned mask = __ballot_sync(FULL, gt);
+            cnt += __popc(mask);
+            const bool le = (idx < nc) && idx != occ && !gt;
+            if (__any_sync(FULL, le)) break;                 // sorted descending: nothing greater further on
+          }
+          const int ins = k + cnt;
+          if (ins < occ) {
+            // shift keys[ins .. occ-1] up by one, from the top end
+            for (int top = occ; top > ins; top -= 32) {
+              const int idx = top - lane;                     // destination index
+              unsigned long long v = 0ull;
+              if (idx > ins) v = keys[idx - 1];
+              __syncwarp();
+              if (idx > ins) keys[idx] = v;
+              __syncwarp();
+            }
+          } else if (ins > occ) {
+            // shift keys[occ+1 .. ins] down by one, from the bottom end
+            for (int bot = occ; bot < ins; bot += 32) {
+              const int idx = bot + lane;                     // destination index
+              unsigned long long v = 0ull;
+              if (idx < ins) v = keys[idx + 1];
+              __syncwarp();
+              if (idx < ins) keys[idx] = v;
+              __syncwarp();
+            }
+          }
+          if (lane == 0) {
+            keys[ins] = nkey;
+            if (x >= tail0 && x < m) atomicOr(flags + ((x - tail0) >> 5), 1u << ((x - tail0) & 31));
+          }
+          __syncwarp();
+        }
+      }
+      // next flagged slot below b in this word (a re-insertion may have flagged one)
+      bits = flags[w] & ((b == 0) ? 0u : ((1u << b) - 1u));
+    }
+  }
+  return 1;
+}
+
 __device__ int heap_select_closed(unsigned long long *heap, const int n, const int need, const float lose_below, const int maxt,
                                   unsigned long long *keys, const int key_cap, unsigned *pay, const int pay_cap,
-                                  int *ordn, int *s_scratch /* [2] shared ints */) {
+                                  int *ordn, int *s_scratch /* [2] shared ints */, const int p_no_reloc = 0) {
   const int tid = threadIdx.x;
+  int relocated = 0;
   if (n >= 65536 || maxt >= 65536 || !(lose_below > -INFINITY)) return 0;
+  // tail slots (the slots the extractions take their s from) that are the home of a candidate: one bit each, at the end of pay
+  const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
+  unsigned *const flags = pay + pay_cap - fwords;
+  const bool have_flags = (fwords < pay_cap);
   if (tid == 0) { s_scratch[0] = 0; s_scratch[1] = 0; }
+  if (have_flags) for (int i = tid; i < fwords; i += BEAM_THREADS) flags[i] = 0u;
   __syncthreads();
   // 1. candidates (a handle per candidate from a shared counter, one atomic per warp and pass)
   const int H = 31 - __clz(n);
-  const int cap = min(min(key_cap, pay_cap), 65535);
+  const int cap = min(min(key_cap, have_flags ? pay_cap - fwords : pay_cap), 65535);   // the flag words sit behind the payload
   for (int h0 = 1; h0 <= n; h0 += BEAM_THREADS) {
     const int h = h0 + tid;
     unsigned long long e = 0ull;
@@ -696,6 +830,7 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
         }
         keys[ci] = ((unsigned long long)fkey(hval(e)) << 32) | ((unsigned long long)(0xffffu - (unsigned)pre) << 16) | (unsigned)ci;
         pay[ci] = ((unsigned)h << 16) | (unsigned)(e >> 32);
+        if (have_flags && h >= tail0) atomicOr(flags + ((h - tail0) >> 5), 1u << ((h - tail0) & 31));
       }
     }
   }
@@ -703,6 +838,7 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
   const int nc = s_scratch[0];
   int np = 1; while (np < nc) np <<= 1;
   if (nc > cap || np > key_cap || nc < need) return 0;      // uniform: s_scratch[0] is read after the barrier
+  const bool can_relocate = have_flags;
   for (int i = nc + tid; i < np; i += BEAM_THREADS) keys[i] = 0ull;
   __syncthreads();
   // 2. bitonic sort, descending
@@ -731,10 +867,18 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
     if (i + 1 >= kstep + d) s_scratch[1] = 1;
   }
   __syncthreads();
-  if (s_scratch[1]) return 0;
+  if (s_scratch[1]) {
+    // 3b. a tied tail element may still be in its leaf when the leaf is taken: follow the few re-insertions exactly on the
+    //     implicit heap (closed_relocate); warp 0, the others wait
+    if (!can_relocate || p_no_reloc) return 0;
+    if (tid < 32) { const int ok = closed_relocate(keys, nc, n, need, flags, tid); if (tid == 0) s_scratch[1] = ok ? 2 : 1; }
+    __syncthreads();
+    if (s_scratch[1] != 2) return 0;
+    relocated = 1;
+  }
   // 4. survivors in visiting order: last extracted first
   for (int k = tid; k < need; k += BEAM_THREADS) ordn[k] = (int)(pay[(unsigned)keys[need - 1 - k] & 0xffffu] & 0xffffu);
-  return 1;
+  return 1 + relocated;
 }
 
 
@@ -1449,8 +1593,8 @@ beam_kernel_mp(const BeamParams p) {
         if (!p.no_closed) {
           sc.run((int)threadIdx.x, BEAM_THREADS);
           closed = heap_select_closed(heap, ncre, need, lose_below, MAXT, p.heap_g ? smem_q : heap + ncre + 1, p.heap_g ? p.sort_cap : MAXT + 3 - ncre,
-                                      reinterpret_cast<unsigned *>(offs), 2 * (p.beam + 2), ordn, s_cf);
-          if (tid == 0) { atomicAdd(p.misspec_counter + 4, 1ull); if (closed) atomicAdd(p.misspec_counter + 5, 1ull); }
+                                      reinterpret_cast<unsigned *>(offs), 2 * (p.beam + 2), ordn, s_cf, p.no_reloc);
+          if (tid == 0) { atomicAdd(p.misspec_counter + 4, 1ull); if (closed) atomicAdd(p.misspec_counter + 5, 1ull); if (closed == 2) atomicAdd(p.misspec_counter + 6, 1ull); }
         }
         if (!closed) {
           heap_pad_sentinels<true>(heap, ncre, MAXT);
@@ -1879,6 +2023,7 @@ extern "C" int jb200_decoder_create(const jb200_tree_desc *t, jb200_gmm *am, int
     }
   }
   P.chunk = nullptr; P.state = nullptr; P.interim = 0; P.interim_words = nullptr; P.atoms_in_place = 0;
+  P.no_reloc = getenv("JB200_NO_RELOCATE") ? atoi(getenv("JB200_NO_RELOCATE")) : 0;
   P.prof_fine = getenv("JB200_PROF_FINE") ? atoi(getenv("JB200_PROF_FINE")) : 0;   // extra barrier: slot 4 = word-internal expansion alone
   P.no_lose = getenv("JB200_NO_LOSER_CUT") ? atoi(getenv("JB200_NO_LOSER_CUT")) : 0;
   P.no_closed = getenv("JB200_NO_CLOSED_FORM") ? atoi(getenv("JB200_NO_CLOSED_FORM")) : 0;   // 1: always replay the extraction loop
@@ -2165,6 +2310,14 @@ extern "C" int jb200_decoder_select_stats(jb200_decoder *d, int64_t out[2]) {
   JB_CUDA(cudaMemcpy(v, d->P.misspec_counter + 4, sizeof(v), cudaMemcpyDeviceToHost));
   out[0] = (int64_t)v[0]; out[1] = (int64_t)v[1];
   return JB200_OK;
+}
+
+extern "C" int64_t jb200_decoder_relocated_selects(jb200_decoder *d) {
+  if (!d) return -1;
+  unsigned long long v = 0;
+  cudaSetDevice(d->device);
+  if (cudaMemcpy(&v, d->P.misspec_counter + 6, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
 }
 
 extern "C" int64_t jb200_decoder_last_d2h_bytes(const jb200_decoder *d) { return d ? d->last_d2h : 0; }

@@ -50,6 +50,8 @@ def main():
     configs = [
         ("base", resident, 0, {}),
         ("host_numbering", resident, 0, {"JB200_NO_RENUMBER": "1"}),
+        ("no_relocate", resident, 0, {"JB200_NO_RELOCATE": "1"}),
+        ("b3_pipe32", B3, 32, {}),
         ("b3_nopipe", B3, 0, {}),
         ("b3_pipe250", B3, 250, {}),
         ("b3_pipe125", B3, 125, {}),
@@ -96,7 +98,7 @@ def main():
         out = {"config": label, "utts": B, "pipe_frames": pipe, "slices": dec.pipeline_info()["slices"], "ms_per_step": round(wall, 2),
                "frames_per_s": round(B * T / (wall / 1000.0)), "score_exposed_ms": round(float(np.mean(sc)), 2),
                "beam_ms": round(float(np.mean(bm)), 2), "score_busy_ms": round(float(np.mean(busy)), 2), "decoded_ok": f"{ok}/{B}",
-               "fingerprint": fp, "phase_cycles_per_frame": [round(float(x)) for x in phase]}
+               "fingerprint": fp, "phase_cycles_per_frame": [round(float(x)) for x in phase], "cut": dec.heap_stats()}
         print(json.dumps(out), flush=True)
         fps[label] = (fp, (steps - 1) % 2)
         dec.close()

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -247,6 +248,140 @@ static bool closed_dynamic_scan(const std::vector<Ent> &H0, int n, int need, flo
   return true;
 }
 
+// ---- lane-by-lane emulation of closed_relocate (csrc/beam.cu): the same chunks, ballots, done masks and shifts ----------
+typedef unsigned long long u64;
+static unsigned fkey_of(float f) { unsigned b; memcpy(&b, &f, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+static int emu_subtree_size(int c, int n, int H) {
+  const int dc = 31 - __builtin_clz(c);
+  if (dc > H) return 0;
+  const int sh = H - dc;
+  const int first = c << sh, width = 1 << sh;
+  return (width - 1) + std::max(0, std::min(n - first + 1, width));
+}
+static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const int need, std::vector<unsigned> &flags) {
+  const int H = 31 - __builtin_clz(n);
+  const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
+  for (int w = fwords - 1; w >= 0; w--) {
+    unsigned bits = flags[w];
+    while (bits) {
+      const int b = 31 - __builtin_clz(bits);
+      const int m = tail0 + w * 32 + b;
+      const int k = n - m + 1;
+      if (m <= n && m >= 2 && k <= need) {
+        const int dm = 31 - __builtin_clz(m);
+        int j = 0, a = 1, lo = 0, hi = n, occ = -1;
+        for (int base = k - 1; base < nc && occ < 0; base += 32) {
+          unsigned done = 0u;
+          while (true) {
+            unsigned mask = 0u;
+            for (int lane = 0; lane < 32; lane++) {
+              const int idx = base + lane;
+              const u64 key = (idx < nc) ? keys[idx] : 0ull;
+              const int pre = 0xffff - (int)((key >> 16) & 0xffffu);
+              const bool in = (idx < nc) && pre >= lo && pre < hi && !((done >> lane) & 1u);
+              if (in) mask |= 1u << lane;
+            }
+            if (!mask) break;
+            const int f = __builtin_ffs(mask) - 1;
+            if (j == dm) { occ = base + f; break; }
+            j++;
+            const int nxt = m >> (dm - j);
+            const int lsz = emu_subtree_size(2 * a, n, H);
+            if (nxt == 2 * a) { lo = lo + 1; hi = lo + lsz; } else { lo = lo + 1 + lsz; }
+            a = nxt;
+            done |= (f >= 31) ? 0xffffffffu : ((2u << f) - 1u);
+          }
+        }
+        if (occ >= k) {
+          const u64 ekey = keys[occ];
+          const unsigned esc = (unsigned)(ekey >> 32);
+          const int msz = m - 1;
+          int x = 1; lo = 0; hi = n;
+          bool stop = (2 * x > msz);
+          for (int base = k; base < nc && !stop; base += 32) {
+            unsigned done = 0u;
+            while (!stop) {
+              unsigned mask = 0u;
+              for (int lane = 0; lane < 32; lane++) {
+                const int idx = base + lane;
+                const u64 key = (idx < nc) ? keys[idx] : 0ull;
+                const int pre = 0xffff - (int)((key >> 16) & 0xffffu);
+                const bool in = (idx < nc) && idx != occ && pre >= lo && pre < hi && !((done >> lane) & 1u);
+                if (in) mask |= 1u << lane;
+              }
+              if (!mask) break;
+              const int f = __builtin_ffs(mask) - 1;
+              const u64 fk = keys[base + f];
+              const unsigned osc = (unsigned)(fk >> 32);
+              const int opre = 0xffff - (int)((fk >> 16) & 0xffffu);
+              if (opre == lo) return 0;
+              if (esc >= osc) { stop = true; break; }
+              const int lsz = emu_subtree_size(2 * x, n, H);
+              if (opre < lo + 1 + lsz) { x = 2 * x; lo = lo + 1; hi = lo + lsz; }
+              else { x = 2 * x + 1; lo = lo + 1 + lsz; }
+              if (2 * x > msz) { stop = true; break; }
+              done |= (f >= 31) ? 0xffffffffu : ((2u << f) - 1u);
+            }
+          }
+          const u64 nkey = (ekey & 0xffffffff0000ffffull) | ((u64)(0xffffu - (unsigned)lo) << 16);
+          int cnt = 0;
+          for (int base = k; base < nc; base += 32) {
+            bool any_le = false;
+            for (int lane = 0; lane < 32; lane++) {
+              const int idx = base + lane;
+              const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
+              if (gt) cnt++;
+              if ((idx < nc) && idx != occ && !gt) any_le = true;
+            }
+            if (any_le) break;
+          }
+          const int ins = k + cnt;
+          if (ins < occ) {
+            for (int top = occ; top > ins; top -= 32) {
+              u64 v[32];
+              for (int lane = 0; lane < 32; lane++) { const int idx = top - lane; v[lane] = (idx > ins) ? keys[idx - 1] : 0ull; }
+              for (int lane = 0; lane < 32; lane++) { const int idx = top - lane; if (idx > ins) keys[idx] = v[lane]; }
+            }
+          } else if (ins > occ) {
+            for (int bot = occ; bot < ins; bot += 32) {
+              u64 v[32];
+              for (int lane = 0; lane < 32; lane++) { const int idx = bot + lane; v[lane] = (idx < ins) ? keys[idx + 1] : 0ull; }
+              for (int lane = 0; lane < 32; lane++) { const int idx = bot + lane; if (idx < ins) keys[idx] = v[lane]; }
+            }
+          }
+          keys[ins] = nkey;
+          if (x >= tail0 && x < m) flags[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31);
+        }
+      }
+      bits = flags[w] & ((b == 0) ? 0u : ((1u << b) - 1u));
+    }
+  }
+  return 1;
+}
+// the kernel's heap_select_closed around it: collect, sort descending by the packed key, relocate, read the order off
+static bool closed_emulated(const std::vector<Ent> &H0, int n, int need, float lose_below, std::vector<int> &out) {
+  if (n >= 65536) return false;
+  const int H = 31 - __builtin_clz(n);
+  const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
+  std::vector<unsigned> flags(fwords, 0u), pay;
+  std::vector<u64> keys;
+  for (int h = 1; h <= n; h++) if (H0[h].v >= lose_below) {
+    int pre = 0, cur = 1;
+    for (int bb = (31 - __builtin_clz(h)) - 1; bb >= 0; bb--) { const int bit = (h >> bb) & 1; pre += 1 + (bit ? emu_subtree_size(cur * 2, n, H) : 0); cur = cur * 2 + bit; }
+    const int ci = (int)keys.size();
+    keys.push_back(((u64)fkey_of(H0[h].v) << 32) | ((u64)(0xffffu - (unsigned)pre) << 16) | (unsigned)ci);
+    pay.push_back(((unsigned)h << 16) | (unsigned)H0[h].id);
+    if (h >= tail0) flags[(h - tail0) >> 5] |= 1u << ((h - tail0) & 31);
+  }
+  const int nc = (int)keys.size();
+  if (nc < need || nc > 65535) return false;
+  std::sort(keys.begin(), keys.end(), std::greater<u64>());
+  if (!emu_relocate(keys, nc, n, need, flags)) return false;
+  out.resize(need);
+  for (int k = 0; k < need; k++) out[k] = (int)(pay[(unsigned)keys[k] & 0xffffu] & 0xffffu);
+  return true;
+}
+
 static int run_one(std::vector<Ent> A, int n, int need, float lose_below, long &bad) {
   heap_build(A, n);
   std::vector<int> ref, dyn;
@@ -256,6 +391,9 @@ static int run_one(std::vector<Ent> A, int n, int need, float lose_below, long &
   std::vector<int> dyn2;
   if (!closed_dynamic_scan(A, n, need, lose_below, dyn2)) { bad++; return -1000000; }
   for (int k = 0; k < need; k++) if (ref[k] != dyn2[k]) { bad++; return -(k + 1) - 2000000; }
+  std::vector<int> dyn3;
+  if (!closed_emulated(A, n, need, lose_below, dyn3)) { bad++; return -3000000; }
+  for (int k = 0; k < need; k++) if (ref[k] != dyn3[k]) { bad++; return -(k + 1) - 4000000; }
   return 1;
 }
 
