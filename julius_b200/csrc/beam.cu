@@ -684,7 +684,8 @@ __device__ __forceinline__ int closed_subtree_size(const int c, const int n, con
 //   * e's key gets the landing slot's pre-order position and moves to its place in the order (behind this step's root).
 // tools/heapdyn.cpp is the CPU model (closed_dynamic_scan), exact on recorded cuts of real decodes and on random heaps
 // with as few as 8 distinct scores.  One warp; returns 0 on anything unexpected (the caller replays the loop instead).
-__device__ __noinline__ int closed_relocate(unsigned long long *keys, const int nc, const int n, const int need, unsigned *flags, const int lane) {
+__device__ __noinline__ int closed_relocate(unsigned long long *keys, const int nc, const int n, const int need, unsigned *flags, unsigned *multi,
+                                            unsigned *pay, const int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   const int H = 31 - __clz(n);
   const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
@@ -696,9 +697,11 @@ __device__ __noinline__ int closed_relocate(unsigned long long *keys, const int 
       const int k = n - m + 1;                              // step; this step's root is keys[k-1]
       if (m <= n && m >= 2 && k <= need) {
         const int dm = 31 - __clz(m);
+        const bool is_multi = (multi[(m - tail0) >> 5] >> ((m - tail0) & 31)) & 1u;    // a re-inserted element landed in this leaf too
         // --- the occupant of leaf m
         int j = 0, a = 1, lo = 0, hi = n, occ = -1;
-        for (int base = k - 1; base < nc && occ < 0; base += 32) {
+        bool gone = false;
+        for (int base = k - 1; base < nc && occ < 0 && !gone; base += 32) {
           const int idx = base + lane;
           const unsigned long long key = (idx < nc) ? keys[idx] : 0ull;
           const int pre = 0xffff - (int)((key >> 16) & 0xffffu);
@@ -709,6 +712,8 @@ __device__ __noinline__ int closed_relocate(unsigned long long *keys, const int 
             if (!mask) break;
             const int f = __ffs(mask) - 1;
             if (j == dm) { occ = base + f; break; }
+            // the leaf's own candidate, pulled up to level j: only a loser can be in the leaf now
+            if (!is_multi && (int)(pay[(unsigned)keys[base + f] & 0xffffu] >> 16) == m) { gone = true; break; }
             j++;
             const int nxt = m >> (dm - j);
             const int lsz = closed_subtree_size(2 * a, n, H);
@@ -748,14 +753,26 @@ __device__ __noinline__ int closed_relocate(unsigned long long *keys, const int 
           }
           // --- e's home is x (pre-order position lo): new key, new place among the alive elements behind this step's root
           const unsigned long long nkey = (ekey & 0xffffffff0000ffffull) | ((unsigned long long)(0xffffu - (unsigned)lo) << 16);
+          // the new place is inside e's tie group: one window around occ, unless the group is wider than that
           int cnt = 0;
-          for (int base = k; base < nc; base += 32) {
-            const int idx = base + lane;
-            const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
-            const unsigned mask = __ballot_sync(FULL, gt);
-            cnt += __popc(mask);
-            const bool le = (idx < nc) && idx != occ && !gt;
-            if (__any_sync(FULL, le)) break;                 // sorted descending: nothing greater further on
+          {
+            const int wb = max(k, occ - 16), we = wb + 31;
+            const bool lo_ok = (wb == k) || ((unsigned)(keys[wb] >> 32) > esc);
+            const bool hi_ok = (we >= nc) || ((unsigned)(keys[we] >> 32) < esc);
+            if (lo_ok && hi_ok) {
+              const int idx = wb + lane;
+              const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
+              cnt = (wb - k) + __popc(__ballot_sync(FULL, gt));
+            } else {
+              for (int base = k; base < nc; base += 32) {
+                const int idx = base + lane;
+                const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
+                const unsigned mask = __ballot_sync(FULL, gt);
+                cnt += __popc(mask);
+                const bool le = (idx < nc) && idx != occ && !gt;
+                if (__any_sync(FULL, le)) break;             // sorted descending: nothing greater further on
+              }
+            }
           }
           const int ins = k + cnt;
           if (ins < occ) {
@@ -781,7 +798,9 @@ __device__ __noinline__ int closed_relocate(unsigned long long *keys, const int 
           }
           if (lane == 0) {
             keys[ins] = nkey;
-            if (x >= tail0 && x < m) atomicOr(flags + ((x - tail0) >> 5), 1u << ((x - tail0) & 31));
+            unsigned *pp = pay + ((unsigned)nkey & 0xffffu);
+            *pp = ((unsigned)x << 16) | (*pp & 0xffffu);        // home slot of the candidate
+            if (x >= tail0 && x < m) { flags[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31); multi[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31); }
           }
           __syncwarp();
         }
@@ -800,15 +819,16 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
   int relocated = 0;
   if (n >= 65536 || maxt >= 65536 || !(lose_below > -INFINITY)) return 0;
   // tail slots (the slots the extractions take their s from) that are the home of a candidate: one bit each, at the end of pay
+  // (a second bit per slot: a re-inserted element has landed there as well)
   const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
-  unsigned *const flags = pay + pay_cap - fwords;
-  const bool have_flags = (fwords < pay_cap);
+  unsigned *const flags = pay + pay_cap - fwords, *const multi = pay + pay_cap - 2 * fwords;
+  const bool have_flags = (2 * fwords < pay_cap);
   if (tid == 0) { s_scratch[0] = 0; s_scratch[1] = 0; }
-  if (have_flags) for (int i = tid; i < fwords; i += BEAM_THREADS) flags[i] = 0u;
+  if (have_flags) for (int i = tid; i < 2 * fwords; i += BEAM_THREADS) multi[i] = 0u;
   __syncthreads();
   // 1. candidates (a handle per candidate from a shared counter, one atomic per warp and pass)
   const int H = 31 - __clz(n);
-  const int cap = min(min(key_cap, have_flags ? pay_cap - fwords : pay_cap), 65535);   // the flag words sit behind the payload
+  const int cap = min(min(key_cap, have_flags ? pay_cap - 2 * fwords : pay_cap), 65535);   // the flag words sit behind the payload
   for (int h0 = 1; h0 <= n; h0 += BEAM_THREADS) {
     const int h = h0 + tid;
     unsigned long long e = 0ull;
@@ -830,7 +850,6 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
         }
         keys[ci] = ((unsigned long long)fkey(hval(e)) << 32) | ((unsigned long long)(0xffffu - (unsigned)pre) << 16) | (unsigned)ci;
         pay[ci] = ((unsigned)h << 16) | (unsigned)(e >> 32);
-        if (have_flags && h >= tail0) atomicOr(flags + ((h - tail0) >> 5), 1u << ((h - tail0) & 31));
       }
     }
   }
@@ -853,25 +872,32 @@ __device__ int heap_select_closed(unsigned long long *heap, const int n, const i
       __syncthreads();
     }
   }
-  // 3. the test: no tail element that ties with another candidate can still be in its slot when the slot is taken
+  // 3. the test: which tail candidates may still be in their leaf when it is taken?  If slot p still held e at step
+  //    k = n-p+1, the k-1 elements extracted so far and the d = depth(p) elements above p would all be ahead of e, so
+  //    rank(e) >= k + d.  The rank of an element changes only when an element of its own score is re-inserted, so an untied
+  //    e with rank < k + d is gone for sure, and a tied one if even the last place of its tie group is < k + d.  The others
+  //    are flagged; if none of the flagged ties with anybody no re-insertion can matter (the plain closed form is exact).
   const unsigned theta = (unsigned)(keys[need - 1] >> 32);
   for (int i = tid; i < nc; i += BEAM_THREADS) {
     const unsigned long long ki = keys[i];
     const unsigned sk = (unsigned)(ki >> 32);
     if (sk < theta) continue;
-    const bool tied = (i > 0 && (unsigned)(keys[i - 1] >> 32) == sk) || (i + 1 < nc && (unsigned)(keys[i + 1] >> 32) == sk);
-    if (!tied) continue;
     const int slot = (int)(pay[(unsigned)ki & 0xffffu] >> 16);
-    if (slot < n - need + 1) continue;
+    if (slot < tail0) continue;
+    const bool tied = (i > 0 && (unsigned)(keys[i - 1] >> 32) == sk) || (i + 1 < nc && (unsigned)(keys[i + 1] >> 32) == sk);
+    int last = i;
+    if (tied) { int g = 0; while (last + 1 < nc && (unsigned)(keys[last + 1] >> 32) == sk && g < 8) { last++; g++; } if (g == 8) last = nc; }
     const int kstep = n - slot + 1, d = 31 - __clz(slot);
-    if (i + 1 >= kstep + d) s_scratch[1] = 1;
+    if (last + 1 < kstep + d) continue;
+    if (have_flags) atomicOr(flags + ((slot - tail0) >> 5), 1u << ((slot - tail0) & 31));
+    if (tied) s_scratch[1] = 1;
   }
   __syncthreads();
   if (s_scratch[1]) {
     // 3b. a tied tail element may still be in its leaf when the leaf is taken: follow the few re-insertions exactly on the
     //     implicit heap (closed_relocate); warp 0, the others wait
     if (!can_relocate || p_no_reloc) return 0;
-    if (tid < 32) { const int ok = closed_relocate(keys, nc, n, need, flags, tid); if (tid == 0) s_scratch[1] = ok ? 2 : 1; }
+    if (tid < 32) { const int ok = closed_relocate(keys, nc, n, need, flags, multi, pay, tid); if (tid == 0) s_scratch[1] = ok ? 2 : 1; }
     __syncthreads();
     if (s_scratch[1] != 2) return 0;
     relocated = 1;

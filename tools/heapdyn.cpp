@@ -258,7 +258,8 @@ static int emu_subtree_size(int c, int n, int H) {
   const int first = c << sh, width = 1 << sh;
   return (width - 1) + std::max(0, std::min(n - first + 1, width));
 }
-static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const int need, std::vector<unsigned> &flags) {
+static long g3_chunks = 0, g3_checks = 0, g3_events = 0, g3_frames = 0, g3_ch_occ_event = 0, g3_ch_occ_gone = 0, g3_ch_occ_none = 0, g3_n_gone = 0, g3_n_none = 0, g3_ch_chain = 0, g3_ch_cnt = 0;
+static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const int need, std::vector<unsigned> &flags, std::vector<unsigned> &multi, std::vector<unsigned> &pay) {
   const int H = 31 - __builtin_clz(n);
   const int tail0 = n - need + 1, fwords = (need + 31) >> 5;
   for (int w = fwords - 1; w >= 0; w--) {
@@ -269,9 +270,14 @@ static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const
       const int k = n - m + 1;
       if (m <= n && m >= 2 && k <= need) {
         const int dm = 31 - __builtin_clz(m);
+        const bool is_multi = (multi[(m - tail0) >> 5] >> ((m - tail0) & 31)) & 1u;
         int j = 0, a = 1, lo = 0, hi = n, occ = -1;
-        for (int base = k - 1; base < nc && occ < 0; base += 32) {
+        bool gone = false;
+        g3_checks++;
+        const long c0 = g3_chunks;
+        for (int base = k - 1; base < nc && occ < 0 && !gone; base += 32) {
           unsigned done = 0u;
+          g3_chunks++;
           while (true) {
             unsigned mask = 0u;
             for (int lane = 0; lane < 32; lane++) {
@@ -284,6 +290,9 @@ static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const
             if (!mask) break;
             const int f = __builtin_ffs(mask) - 1;
             if (j == dm) { occ = base + f; break; }
+            // the leaf's own candidate, pulled up to level j: nothing but a loser can be in the leaf (unless a re-inserted
+            // element landed there too)
+            if (!is_multi && (int)(pay[(unsigned)keys[base + f] & 0xffffu] >> 16) == m) { gone = true; break; }
             j++;
             const int nxt = m >> (dm - j);
             const int lsz = emu_subtree_size(2 * a, n, H);
@@ -292,14 +301,18 @@ static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const
             done |= (f >= 31) ? 0xffffffffu : ((2u << f) - 1u);
           }
         }
+        if (occ >= k) g3_ch_occ_event += g3_chunks - c0; else if (gone) { g3_ch_occ_gone += g3_chunks - c0; g3_n_gone++; } else { g3_ch_occ_none += g3_chunks - c0; g3_n_none++; }
         if (occ >= k) {
+          const long c1 = g3_chunks;
           const u64 ekey = keys[occ];
           const unsigned esc = (unsigned)(ekey >> 32);
+          g3_events++;
           const int msz = m - 1;
           int x = 1; lo = 0; hi = n;
           bool stop = (2 * x > msz);
           for (int base = k; base < nc && !stop; base += 32) {
             unsigned done = 0u;
+            g3_chunks++;
             while (!stop) {
               unsigned mask = 0u;
               for (int lane = 0; lane < 32; lane++) {
@@ -323,17 +336,32 @@ static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const
               done |= (f >= 31) ? 0xffffffffu : ((2u << f) - 1u);
             }
           }
+          g3_ch_chain += g3_chunks - c1;
           const u64 nkey = (ekey & 0xffffffff0000ffffull) | ((u64)(0xffffu - (unsigned)lo) << 16);
+          // the new place is inside e's tie group: one window around occ, unless the group is wider than that
           int cnt = 0;
-          for (int base = k; base < nc; base += 32) {
-            bool any_le = false;
-            for (int lane = 0; lane < 32; lane++) {
-              const int idx = base + lane;
-              const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
-              if (gt) cnt++;
-              if ((idx < nc) && idx != occ && !gt) any_le = true;
+          {
+            const int wb = std::max(k, occ - 16);
+            const bool lo_ok = (wb == k) || ((unsigned)(keys[wb] >> 32) > esc);
+            const int we = wb + 31;
+            const bool hi_ok = (we >= nc) || ((unsigned)(keys[we] >> 32) < esc);
+            g3_ch_cnt++;
+            if (lo_ok && hi_ok) {
+              cnt = wb - k;
+              for (int lane = 0; lane < 32; lane++) { const int idx = wb + lane; if (idx < nc && idx != occ && keys[idx] > nkey) cnt++; }
+            } else {
+              for (int base = k; base < nc; base += 32) {
+                bool any_le = false;
+                g3_ch_cnt++;
+                for (int lane = 0; lane < 32; lane++) {
+                  const int idx = base + lane;
+                  const bool gt = (idx < nc) && idx != occ && keys[idx] > nkey;
+                  if (gt) cnt++;
+                  if ((idx < nc) && idx != occ && !gt) any_le = true;
+                }
+                if (any_le) break;
+              }
             }
-            if (any_le) break;
           }
           const int ins = k + cnt;
           if (ins < occ) {
@@ -350,7 +378,8 @@ static int emu_relocate(std::vector<u64> &keys, const int nc, const int n, const
             }
           }
           keys[ins] = nkey;
-          if (x >= tail0 && x < m) flags[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31);
+          { unsigned &pp = pay[(unsigned)nkey & 0xffffu]; pp = ((unsigned)x << 16) | (pp & 0xffffu); }
+          if (x >= tail0 && x < m) { flags[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31); multi[(x - tail0) >> 5] |= 1u << ((x - tail0) & 31); }
         }
       }
       bits = flags[w] & ((b == 0) ? 0u : ((1u << b) - 1u));
@@ -371,12 +400,29 @@ static bool closed_emulated(const std::vector<Ent> &H0, int n, int need, float l
     const int ci = (int)keys.size();
     keys.push_back(((u64)fkey_of(H0[h].v) << 32) | ((u64)(0xffffu - (unsigned)pre) << 16) | (unsigned)ci);
     pay.push_back(((unsigned)h << 16) | (unsigned)H0[h].id);
-    if (h >= tail0) flags[(h - tail0) >> 5] |= 1u << ((h - tail0) & 31);
   }
   const int nc = (int)keys.size();
   if (nc < need || nc > 65535) return false;
   std::sort(keys.begin(), keys.end(), std::greater<u64>());
-  if (!emu_relocate(keys, nc, n, need, flags)) return false;
+  // which tail candidates may still be in their leaf when it is taken (the kernel's test loop)
+  std::vector<unsigned> multi(fwords, 0u);
+  bool need_reloc = false;
+  const unsigned theta = (unsigned)(keys[need - 1] >> 32);
+  for (int i = 0; i < nc; i++) {
+    const unsigned sk = (unsigned)(keys[i] >> 32);
+    if (sk < theta) continue;
+    const int slot = (int)(pay[(unsigned)keys[i] & 0xffffu] >> 16);
+    if (slot < tail0) continue;
+    const int kstep = n - slot + 1, dd = 31 - __builtin_clz(slot);
+    const bool tied = (i > 0 && (unsigned)(keys[i - 1] >> 32) == sk) || (i + 1 < nc && (unsigned)(keys[i + 1] >> 32) == sk);
+    int last = i;                                   // last index of the tie group (bounded look-ahead; beyond it: assume the worst)
+    if (tied) { int g = 0; while (last + 1 < nc && (unsigned)(keys[last + 1] >> 32) == sk && g < 8) { last++; g++; } if (g == 8) last = nc; }
+    if (last + 1 < kstep + dd) continue;            // cannot be in its slot any more, wherever in its tie group it ends up
+    flags[(slot - tail0) >> 5] |= 1u << ((slot - tail0) & 31);
+    if (tied) need_reloc = true;
+  }
+  g3_frames++;
+  if (need_reloc && !emu_relocate(keys, nc, n, need, flags, multi, pay)) return false;
   out.resize(need);
   for (int k = 0; k < need; k++) out[k] = (int)(pay[(unsigned)keys[k] & 0xffffu] & 0xffffu);
   return true;
@@ -416,6 +462,9 @@ static int dump_mode(const char *path) {
   }
   printf("upward selects %ld: mismatches %ld; per select: %.1f leaf checks, %.1f re-insertions, %.1f subtree queries; scan form: %.0f elements visited\n", nup, bad,
          (double)g_checks / std::max(1L, g_frames), (double)g_events / std::max(1L, g_frames), (double)g_levels / std::max(1L, g_frames), (double)g2_scan_elems / std::max(1L, g_frames));
+  printf("kernel form: %.1f leaf checks, %.1f re-insertions, %.1f 32-key chunks per select\n", (double)g3_checks / std::max(1L, g3_frames), (double)g3_events / std::max(1L, g3_frames), (double)g3_chunks / std::max(1L, g3_frames));
+  printf("  chunks per select: occupant scans that end in an event %.1f, in 'pulled up' %.1f (%.1f scans), in 'nobody' %.1f (%.1f scans); chain walks %.1f; insert-position counts %.1f\n",
+         (double)g3_ch_occ_event / g3_frames, (double)g3_ch_occ_gone / g3_frames, (double)g3_n_gone / g3_frames, (double)g3_ch_occ_none / g3_frames, (double)g3_n_none / g3_frames, (double)g3_ch_chain / g3_frames, (double)g3_ch_cnt / g3_frames);
   return bad != 0;
 }
 
@@ -442,5 +491,6 @@ int main(int argc, char **argv) {
   }
   printf("trials %ld, mismatches %ld; per select: %.1f leaf checks, %.1f re-insertions, %.1f subtree queries; scan form: %.0f elements visited\n", ran, bad,
          (double)g_checks / std::max(1L, g_frames), (double)g_events / std::max(1L, g_frames), (double)g_levels / std::max(1L, g_frames), (double)g2_scan_elems / std::max(1L, g_frames));
+  printf("kernel form: %.1f leaf checks, %.1f re-insertions, %.1f 32-key chunks per select\n", (double)g3_checks / std::max(1L, g3_frames), (double)g3_events / std::max(1L, g3_frames), (double)g3_chunks / std::max(1L, g3_frames));
   return bad != 0;
 }
