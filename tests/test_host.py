@@ -114,3 +114,21 @@ def test_nothing_in_the_product_imports_the_oracle():
             if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "liboracle" in txt or "oracle/restate" in txt or '#include "oracle' in txt:
                 bad.append(os.path.relpath(os.path.join(dirpath, fn), ROOT))
     assert not bad, bad
+
+
+def test_user_lm_export_limits_are_loud(tmp_path):
+    """-userlm is tabulated densely over the dictionary by the export step: a dictionary above the limit must make the
+    start-up fail with a message, not produce a model that silently ignores the user functions."""
+    import os
+    import pytest
+    from oracle import ffi, fixtures
+    if not ffi.have_ref():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path)
+    with pytest.raises(RuntimeError):
+        fixtures.make_fixture("small", d, n_utts=1, n_frames=50, extra_args=["-userlm", "-b", "60"],
+                              env_extra={"JREF_USERLM": "1", "JB200_USERLM_MAXWORDS": "100"})
+    # within the limit the same call exports (402 words)
+    m, files, dump, out = fixtures.make_fixture("small", d, n_utts=1, n_frames=50, extra_args=["-userlm", "-b", "60"],
+                                                env_extra={"JREF_USERLM": "1"})
+    assert os.path.getsize(os.path.join(d, "model.jb2m")) > 402 * 402 * 8

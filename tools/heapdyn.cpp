@@ -476,7 +476,8 @@ int main(int argc, char **argv) {
   srand(1);
   long bad = 0, ran = 0;
   for (int tr = 0; tr < trials; tr++) {
-    const int n = 3 + rand() % 2600;
+    const int nmax = getenv("HEAPDYN_NMAX") ? atoi(getenv("HEAPDYN_NMAX")) : 2600;
+    const int n = 3 + rand() % nmax;
     int need = 1 + rand() % (n - 1);
     if (!(need < n - need)) need = std::max(1, (n - 1) / 2 - rand() % std::max(1, n / 4));
     if (!(need < n - need) || need < 1) continue;
