@@ -92,8 +92,9 @@ int jb200_dnn_score_host(jb200_dnn *h, const float *in, int T, float *scores);
  *   outprob_style()                                         libjulius/src/outprob_style.c:354-494
  *   max_successor_prob(_iw)()                               libjulius/src/factoring_sub.c:942-1143
  *   bt_store/bt_relocate_rw/bt_sort_rw                      libjulius/src/backtrellis.c:190-267,438-478
- * run for a whole BATCH of utterances, one thread-block per utterance, all frames
- * inside one persistent kernel.
+ * run for a whole BATCH of utterances, one thread-block per utterance; a launch covers all frames of the
+ * utterances, or one time slice of them (batch pipeline, streams: see the end of this header) -- the kernels are
+ * resumable, an utterance's state lives in its device work area between launches.
  * ---------------------------------------------------------------------------------- */
 typedef struct jb200_decoder jb200_decoder;
 
