@@ -18,7 +18,7 @@ def main():
     name, out = sys.argv[1], sys.argv[2]
     n_utts = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     T = int(sys.argv[4]) if len(sys.argv) > 4 else 300
-    ds = D.Descriptors(refdump.load_blob(workload.path(name, "model.jb2m")))
+    ds = D.Descriptors(workload.load_model(name))
     m = workload.synth_model(name)
     feats = workload.sample_inputs(name, m, n_utts, T, seed=4242)
     lib = ffi.lib()
